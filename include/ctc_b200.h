@@ -1,0 +1,141 @@
+/*
+ * ctc_b200.h -- C ABI of libctc_b200.so: the CTC loss / gradient / Hessian hot path of
+ * alexeytochin/tf_seq2seq_losses rebuilt as hand-written CUDA kernels for NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI of its own (it is Python over TensorFlow ops); each entry point below replaces the
+ * reference *Python* interface cited beside it (paths relative to the reference repository root) and is what a
+ * TensorFlow custom op (tf_seq2seq_losses_b200/tf_adapter/ctc_b200_tf_op.cc), a ctypes binding
+ * (tf_seq2seq_losses_b200/_lib.py) or any other host would bind.  See INTEGRATION.md.
+ *
+ * Contract (all device entry points):
+ *   - every pointer is a DEVICE pointer owned by the caller, including the workspace; the library never
+ *     allocates, frees or synchronises; all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - inputs are read-only, outputs are fully overwritten (rows t >= logit_length and infeasible samples are
+ *     written as exact zeros, their loss as +inf);
+ *   - return value: CTCB200_OK (0) or a negative error code, never an exception / abort;
+ *   - re-entrant: no mutable global state except one-time per-device kernel attribute caching; safe to call
+ *     concurrently on different streams / devices.
+ * Shapes: logits float32 [B,T,V] batch-major contiguous; labels int32 [B,Lw]; label_length, logit_length int32 [B].
+ * All arithmetic is fp32 (the reference asserts float32, tf_seq2seq_losses/base_loss.py:131).
+ */
+#ifndef CTC_B200_H_
+#define CTC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTCB200_VERSION 100 /* 0.1.0 */
+
+/* variant: which data class of the reference is being replaced */
+#define CTCB200_CLASSIC 0    /* ClassicCtcLossData,    tf_seq2seq_losses/classic_ctc_loss.py:73-669 */
+#define CTCB200_SIMPLIFIED 1 /* SimplifiedCtcLossData, tf_seq2seq_losses/simplified_ctc_loss.py:70-534 */
+
+/* flags */
+#define CTCB200_INPUT_LOGPROBAS 1u /* `logits` already holds log-probabilities (ctc_loss_from_logproba,
+                                      base_loss.py:71-99, and the data-class constructors, base_loss.py:105-114):
+                                      the log-softmax of tools.py:27-40 is skipped */
+
+/* Profiling aid: flags bits 8..15 select which stages of ctcb200_loss_grad are enqueued (bit 8+i = i-th name of
+ * ctcb200_stage_names()); 0 = all.  A partial call must follow a full call on the same workspace and inputs. */
+#define CTCB200_STAGE_SHIFT 8
+#define CTCB200_STAGE_MASK 0xFF00u
+
+/* error codes */
+#define CTCB200_OK 0
+#define CTCB200_ERR_NULL_POINTER (-1)
+#define CTCB200_ERR_BAD_DESCRIPTOR (-2)
+#define CTCB200_ERR_WORKSPACE_TOO_SMALL (-3)
+#define CTCB200_ERR_UNSUPPORTED_SIZE (-4) /* U > 512 states or V > 32768 tokens */
+#define CTCB200_ERR_CUDA (-5)             /* launch failure; cudaGetLastError() was consumed */
+#define CTCB200_ERR_MISALIGNED (-6)       /* workspace not 256-byte aligned */
+
+/* what a workspace is sized for */
+#define CTCB200_WS_LOSS_GRAD 0
+#define CTCB200_WS_STATES 1
+#define CTCB200_WS_HESSIAN 2
+
+typedef struct ctcb200_desc {
+  int32_t B;       /* batch size                      (>= 0) */
+  int32_t T;       /* logits.shape[1]                 (>= 0) */
+  int32_t V;       /* number of tokens incl. blank    (>= 1) */
+  int32_t Lw;      /* labels.shape[1]                 (>= 0) */
+  int32_t blank;   /* blank index, 0 <= blank < V     (base_loss.py:122-125) */
+  int32_t variant; /* CTCB200_CLASSIC | CTCB200_SIMPLIFIED */
+  int32_t U;       /* max_b(label_length)+1 = the reference's max_label_length_plus_one (base_loss.py:478-486);
+                      0 => use Lw+1 (label_length is then clamped to Lw) */
+  uint32_t flags;  /* CTCB200_INPUT_LOGPROBAS | ... */
+} ctcb200_desc;
+
+int ctcb200_version(void);
+const char* ctcb200_strerror(int code);
+
+/* Comma-separated stage (kernel) names of ctcb200_loss_grad, and the number of kernels one full call enqueues. */
+const char* ctcb200_stage_names(void);
+int ctcb200_launches_per_call(const ctcb200_desc* desc);
+
+/* Bytes of device workspace needed by the entry point named by `what` (CTCB200_WS_*); 0 on a bad descriptor. */
+size_t ctcb200_workspace_bytes(const ctcb200_desc* desc, int what);
+
+/*
+ * Fused loss + gradient.  Replaces classic_ctc_loss / simplified_ctc_loss followed by tape.gradient
+ * (tf_seq2seq_losses/classic_ctc_loss.py:33-70, simplified_ctc_loss.py:32-67, base_loss.py:38-99 and the
+ * forward_fn/gradient_fn custom gradients base_loss.py:140-175, gradient base_loss.py:262-298).
+ *   d_loss         [B] upstream gradient of the per-sample loss, or NULL for all-ones
+ *   loss           [B] out: per-sample loss, +inf when the label cannot be emitted
+ *   grad_logits    [B,T,V] out or NULL: d(sum_b d_loss[b]*loss[b]) / d logits  (= d_loss*(softmax*sum(occ) - occ))
+ *   grad_logprobas [B,T,V] out or NULL: d_loss * ClassicCtcLossData.gradient   (= -d_loss*occupancy, base_loss.py:268)
+ */
+int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                      const int32_t* label_length, const int32_t* logit_length, const float* d_loss, float* loss,
+                      float* grad_logits, float* grad_logprobas, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/*
+ * alpha / beta state tensors.  Replaces ClassicCtcLossData.alpha/.beta (classic_ctc_loss.py:310-462, layout
+ * [B,T+1,U,2], s=0 closed / s=1 open) and SimplifiedCtcLossData.alpha/.beta (simplified_ctc_loss.py:291-438,
+ * layout [B,T+1,U]).  desc->U must be the true max(label_length)+1.  alpha, beta or loss may be NULL.
+ */
+int ctcb200_states(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                   const int32_t* label_length, const int32_t* logit_length, float* alpha, float* beta,
+                   float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Dense Hessian of the per-sample loss w.r.t. the log-probabilities, [B,T,V,T,V].  Replaces
+ * BaseCtcLossData.hessian (base_loss.py:186-260) without materialising gamma (classic_ctc_loss.py:167-308,
+ * simplified_ctc_loss.py:85-191).  Also returns loss [B] and gradient [B,T,V] (either may be NULL).
+ */
+int ctcb200_hessian(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                    const int32_t* label_length, const int32_t* logit_length, float* hessian, float* loss,
+                    float* grad_logprobas, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Hessian-vector product: out[b,t,k] = sum_{t',k'} d_gradient[b,t',k'] * hessian[b,t,k,t',k'], the contraction
+ * gradient_fn.backprop performs (base_loss.py:167-173), computed matrix-free.
+ */
+int ctcb200_hvp(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                const int32_t* label_length, const int32_t* logit_length, const float* d_gradient, float* out,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Host-buffer convenience path (what a framework without device tensors, or the end-to-end benchmark, calls):
+ * owns its device buffers, copies the HOST inputs to the device in batch slices on two streams so copies overlap
+ * the kernels, and copies loss (and optionally grad_logits) back.  All pointers are HOST pointers (pinned memory
+ * gives full PCIe bandwidth).  The gradient stays resident on the device (ctcb200_host_grad_device_ptr) unless
+ * host_grad_logits is non-NULL.  Blocks until the results are in the host buffers.
+ */
+typedef struct ctcb200_host_ctx ctcb200_host_ctx;
+int ctcb200_host_create(const ctcb200_desc* desc, int device, int num_slices, ctcb200_host_ctx** out);
+int ctcb200_host_loss_grad(ctcb200_host_ctx* ctx, const float* host_logits, const int32_t* host_labels,
+                           const int32_t* host_label_length, const int32_t* host_logit_length,
+                           float* host_loss, float* host_grad_logits);
+float* ctcb200_host_grad_device_ptr(ctcb200_host_ctx* ctx);
+void ctcb200_host_destroy(ctcb200_host_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTC_B200_H_ */

@@ -1,0 +1,403 @@
+"""Parity of the CUDA path (through the public Python face and the C ABI) against the CPU oracle, the reference's
+known-answer vectors and size-independent properties.  Needs a B200: run with ``-m gpu``.
+
+Tolerances (fp32 kernels vs the fp64 oracle; the reference's own fp32 arithmetic sits in the same band):
+  loss      |d| <= 1e-5 * max(1, |loss|)
+  gradient  max-abs <= 5e-5 for T <= 64 (the reference's 4-places bar), <= 1e-2 for T >= 500
+  Hessian   max-abs <= 1e-5
+  +inf, exact zeros and the 1e10 / 100.0 known answers are compared bit-exactly.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc_oracle as orc
+from tests.ref_cases import CLASSIC, KAT_CASES, README_EXAMPLE, README_GOLDEN, SIMPLIFIED, random_inputs
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_ATOL_SHORT = 5e-5
+GRAD_ATOL_LONG = 1e-2
+HESS_ATOL = 1e-5
+
+
+def _pkg():
+    import tf_seq2seq_losses_b200 as pkg
+    return pkg
+
+
+def _cls(variant):
+    pkg = _pkg()
+    return pkg.ClassicCtcLossData if variant == CLASSIC else pkg.SimplifiedCtcLossData
+
+
+def _fn(variant):
+    pkg = _pkg()
+    return pkg.classic_ctc_loss if variant == CLASSIC else pkg.simplified_ctc_loss
+
+
+def _cuda(a, dtype=None):
+    t = torch.as_tensor(np.asarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def _data_obj(case_or_inputs, variant, blank=0):
+    logits, labels, ll, tl = case_or_inputs
+    logprobas = torch.log_softmax(_cuda(logits, torch.float32), dim=2)
+    return _cls(variant)(labels=_cuda(labels), logprobas=logprobas, label_length=_cuda(ll), logit_length=_cuda(tl),
+                         blank_index=blank), logprobas
+
+
+def _loss_close(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert np.array_equal(np.isinf(got), np.isinf(want)), (got, want)
+    fin = ~np.isinf(want)
+    assert np.all(np.abs(got[fin] - want[fin]) <= LOSS_RTOL * np.maximum(1.0, np.abs(want[fin]))), (got, want)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference's literal known answers, through the data-class surface
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", KAT_CASES, ids=[c["name"] for c in KAT_CASES])
+def test_reference_known_answers(case):
+    # the reference builds logprobas with logit_to_logproba(log(one-hot)) on the host side of the data class
+    logprobas = orc.logit_to_logproba(case["logits"]).astype(np.float32)
+    data = _cls(case["variant"])(labels=_cuda(case["labels"]), logprobas=_cuda(logprobas),
+                                 label_length=_cuda(case["label_length"]), logit_length=_cuda(case["logit_length"]),
+                                 blank_index=torch.tensor(case["blank"], dtype=torch.int32))
+    loss = data.loss.cpu().numpy()
+    if "exp_alpha" in case:
+        assert np.array_equal(np.exp(data.alpha.cpu().numpy()), np.asarray(case["exp_alpha"], dtype=np.float32))
+        assert np.array_equal(np.exp(data.beta.cpu().numpy()), np.asarray(case["exp_beta"], dtype=np.float32))
+    if "loss" in case:
+        if "loss_places" in case:
+            assert np.max(np.abs(loss - np.asarray(case["loss"]))) < 0.5 * 10.0 ** -case["loss_places"]
+        else:
+            assert loss.tolist() == [float(v) for v in case["loss"]]
+    if "loss_below" in case:
+        assert float(loss[0]) < case["loss_below"]
+    if "occupancy" in case:
+        occ = np.exp(data.logarithmic_logproba_gradient.cpu().numpy())
+        assert np.max(np.abs(occ - np.asarray(case["occupancy"]))) < 0.5e-6
+    if "gradient" in case:
+        g = data.gradient.cpu().numpy()
+        if case.get("gradient_exact"):
+            assert np.array_equal(g, np.asarray(case["gradient"], dtype=np.float32))
+        else:
+            assert np.max(np.abs(g - np.asarray(case["gradient"]))) < 0.5e-6
+    if case.get("hessian_zero"):
+        h = data.hessian.cpu().numpy()
+        B, T, V = case["logits"].shape
+        assert h.shape == (B, T, V, T, V)
+        if case.get("gradient_exact"):
+            assert np.array_equal(h, np.zeros_like(h))       # infeasible sample: exact zeros
+        else:
+            assert np.max(np.abs(h)) < 0.5e-6
+
+
+def test_readme_example_loss_gradient_hessian():
+    """BASELINE.json configs[0]: README example, loss + gradient + Hessian (w.r.t. logits, through double backward)."""
+    c = README_EXAMPLE
+    pkg = _pkg()
+    for variant, fn in ((CLASSIC, pkg.classic_ctc_loss), (SIMPLIFIED, pkg.simple_ctc_loss)):
+        logits = _cuda(c["logits"], torch.float32).requires_grad_(True)
+        loss = fn(labels=_cuda(c["labels"]), logits=logits, label_length=_cuda(c["label_length"]),
+                  logit_length=_cuda(c["logit_length"]), blank_index=0)
+        (grad,) = torch.autograd.grad(loss.sum(), logits, create_graph=True)
+        key = "classic" if variant == CLASSIC else "simplified"
+        assert np.allclose(loss.detach().cpu().numpy(), README_GOLDEN[f"{key}_loss"], atol=2e-6)
+        g = grad.detach().cpu().numpy()
+        if variant == CLASSIC:
+            assert np.allclose(g[0], 1 / 3 - np.eye(3)[[1, 2, 0, 2, 1]], atol=2e-6)
+            assert np.allclose(g[1], README_GOLDEN["classic_grad_logits_1"], atol=2e-6)
+        else:
+            assert np.allclose(g[0], README_GOLDEN["simplified_grad_logits_0"], atol=2e-6)
+            assert np.allclose(g[1], README_GOLDEN["simplified_grad_logits_1"], atol=2e-6)
+        # batch_jacobian(gradient, logits) row by row
+        B, T, V = 2, 5, 3
+        H = np.zeros((B, T, V, T, V), dtype=np.float64)
+        for t in range(T):
+            for k in range(V):
+                (row,) = torch.autograd.grad(grad[:, t, k].sum(), logits, retain_graph=True)
+                H[:, t, k] = row.cpu().numpy()
+        data, lp = orc.ctc_loss_data(c["labels"], c["logits"], c["label_length"], c["logit_length"], 0, variant)
+        want = orc.hessian_logits(data, lp)
+        assert np.max(np.abs(H - want)) < HESS_ATOL
+        if variant == CLASSIC:
+            assert abs(np.abs(H).sum() - README_GOLDEN["classic_hessian_logits_abs_sum"]) < 1e-4
+            assert np.allclose(H[1, 0, :, 3, :], np.array([[1, -1, 0], [-1, 1, 0], [0, 0, 0]]) / 49, atol=2e-6)
+            assert np.array_equal(H[1, 4], np.zeros((V, T, V))) and np.array_equal(H[1, :, :, 4], np.zeros((T, V, V)))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# random inputs vs the oracle
+# ------------------------------------------------------------------------------------------------------------------
+SHAPES = [
+    # B, T, V, L, ragged, blank, labels_width
+    (3, 6, 5, 3, True, 0, None),
+    (8, 20, 8, 9, True, 0, 20),        # labels as wide as T, like the reference's generator (tests/common.py:89-94)
+    (8, 64, 10, 30, True, 0, None),    # tests/test_classic_ctc_loss.py:360-393 shape
+    (4, 33, 29, 12, True, 3, None),    # V % 4 != 0 -> scalar row path; non-zero blank
+    (5, 40, 64, 40, False, 63, None),  # T == L: single feasible alignment for the simplified loss
+    (3, 70, 128, 70, True, 0, None),   # U = 71 -> 3 states per lane
+]
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"B{s[0]}T{s[1]}V{s[2]}L{s[3]}" for s in SHAPES])
+def test_loss_and_gradient_match_oracle(shape, variant):
+    B, T, V, L, ragged, blank, lw = shape
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=B * 1000 + T, ragged=ragged, blank=blank, labels_width=lw)
+    d_loss = np.linspace(0.5, 1.5, B).astype(np.float32)
+    want_loss, want_grad, data = orc.loss_and_grad_logits(labels, logits, ll, tl, blank, variant, d_loss=d_loss)
+    x = _cuda(logits).requires_grad_(True)
+    loss = _fn(variant)(_cuda(labels), x, _cuda(ll), _cuda(tl), blank)
+    fin = torch.isfinite(loss)
+    (loss * _cuda(d_loss))[fin].sum().backward()
+    _loss_close(loss.detach().cpu().numpy(), want_loss)
+    got = x.grad.cpu().numpy()
+    want_grad = np.where(np.isinf(want_loss)[:, None, None], 0.0, want_grad)
+    assert np.max(np.abs(got - want_grad)) <= GRAD_ATOL_SHORT
+    # frames beyond logit_length: exact zeros
+    for b in range(B):
+        assert np.array_equal(got[b, tl[b]:], np.zeros_like(got[b, tl[b]:]))
+    # data-class surface on the same inputs
+    obj, _ = _data_obj((logits, labels, ll, tl), variant, blank)
+    assert np.max(np.abs(obj.gradient.cpu().numpy() - data.gradient)) <= GRAD_ATOL_SHORT
+    a, bt = obj.alpha.cpu().numpy(), obj.beta.cpu().numpy()
+    assert a.shape == data.alpha.shape and bt.shape == data.beta.shape
+    for got_s, want_s in ((a, data.alpha), (bt, data.beta)):
+        assert np.array_equal(np.isinf(got_s), np.isinf(want_s))
+        fin_s = ~np.isinf(want_s)
+        assert np.max(np.abs(got_s[fin_s] - want_s[fin_s]) / np.maximum(1.0, np.abs(want_s[fin_s]))) < 1e-5
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_undefined_inputs_do_not_fault(variant):
+    """Inputs the reference leaves undefined: label_length > labels.shape[1] (the reference pads with
+    the blank as a *real* label), a real label equal to the blank, labels >= V or negative, logit_length > T, negative
+    lengths.  The kernels must not fault and must not produce NaN; values are don't-care."""
+    B, T, V, L = 4, 20, 8, 6
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=21, ragged=False, labels_width=4)
+    ll[:] = [6, 5, 2, 3]
+    labels[1, 1] = 0
+    labels[2, 0] = V + 3
+    labels[3, 1] = -2
+    tl[:] = [T + 7, T, -3, T]
+    x = _cuda(logits).requires_grad_(True)
+    loss = _fn(variant)(_cuda(labels), x, _cuda(ll), _cuda(tl), 0)
+    torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)).sum().backward()
+    torch.cuda.synchronize()
+    assert not torch.isnan(loss).any() and not torch.isnan(x.grad).any()
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_edge_samples(variant):
+    """Empty / infeasible / zero-length samples in one batch; -inf and 1e10 logits (BASELINE.json configs[4] edge set)."""
+    B, T, V, L = 6, 12, 16, 5
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=11, ragged=False)
+    logits[0, :, 1:] = -np.inf                     # only the blank is possible -> infeasible for a non-empty label
+    for t in range(T):                             # sample 1: 1e10 on a valid alignment (label, then blanks)
+        logits[1, t, labels[1, t] if t < L else 0] = 1e10
+    labels[1, 1] = labels[1, 0] + 1 if labels[1, 0] + 1 < V else 1   # avoid a repeat so the path is valid for classic
+    logits[1, 1, :] = np.random.default_rng(0).standard_normal(V)
+    logits[1, 1, labels[1, 1]] = 1e10
+    ll[2], tl[2] = 5, 3                            # label longer than the logits -> +inf, zero gradient
+    ll[3] = 0                                      # empty label: loss = -sum log p(blank)
+    tl[4] = 0                                      # no frames: +inf
+    logits[5, 3, 2] = -np.inf                      # a single -inf entry inside a valid row
+    want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, variant)
+    x = _cuda(logits).requires_grad_(True)
+    loss = _fn(variant)(_cuda(labels), x, _cuda(ll), _cuda(tl), 0)
+    torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)).sum().backward()
+    got_loss, got = loss.detach().cpu().numpy(), x.grad.cpu().numpy()
+    assert np.isinf(got_loss[[0, 2, 4]]).all() and np.isinf(want_loss[[0, 2, 4]]).all()
+    _loss_close(got_loss, want_loss)
+    assert not np.isnan(got).any()
+    for b in (0, 2, 4):
+        assert np.array_equal(got[b], np.zeros_like(got[b]))
+    for b in (1, 3, 5):
+        assert np.max(np.abs(got[b] - want_grad[b])) <= GRAD_ATOL_SHORT
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_degenerate_shapes(variant):
+    """tests/test_simplified_ctc_loss.py:322-366, tests/test_classic_ctc_loss.py:309-330: T = 0 and B = 0."""
+    fn = _fn(variant)
+    x = torch.zeros((1, 0, 3), device="cuda", requires_grad=True)
+    loss = fn(_cuda([[1, 2]]), x, _cuda([2]), _cuda([2]), 0)
+    assert loss.tolist() == [float("inf")]
+    (g,) = torch.autograd.grad(loss.sum(), x, allow_unused=True)
+    assert g is None or list(g.shape) == [1, 0, 3]
+    x = torch.zeros((0, 4, 3), device="cuda", requires_grad=True)
+    loss = fn(torch.zeros((0, 2), dtype=torch.int32).cuda(), x, torch.zeros((0,), dtype=torch.int32).cuda(),
+              torch.zeros((0,), dtype=torch.int32).cuda(), 0)
+    assert list(loss.shape) == [0]
+    loss.sum().backward()
+    assert list(x.grad.shape) == [0, 4, 3]
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_hessian_matches_oracle(variant):
+    """ClassicCtcLossData.hessian / SimplifiedCtcLossData.hessian vs the oracle (literal for tiny, matrix-free for cfg-4 shape)."""
+    for (B, T, V, L, seed) in [(2, 4, 3, 2, 0), (2, 6, 5, 3, 1), (3, 50, 32, 15, 2)]:
+        logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
+        if T == 6:
+            labels[0, :2] = 2           # repeated token
+        data, lp = orc.ctc_loss_data(labels, logits, ll, tl, 0, variant)
+        want = data.hessian if T <= 6 else data.hessian_fast()
+        obj, logprobas = _data_obj((logits, labels, ll, tl), variant)
+        got = obj.hessian.cpu().numpy()
+        assert got.shape == want.shape
+        assert np.max(np.abs(got - want)) <= HESS_ATOL
+        # symmetry, tests/test_hessian.py:89-108
+        assert np.max(np.abs(got - np.transpose(got, (0, 3, 4, 1, 2)))) <= 2e-6
+        # matrix-free contraction == dense contraction (gradient_fn.backprop, base_loss.py:167-173)
+        v = np.random.default_rng(seed).standard_normal((B, T, V)).astype(np.float32)
+        hv = obj.hessian_vector_product(_cuda(v)).cpu().numpy()
+        assert np.max(np.abs(hv - np.einsum("btkuj,buj->btk", want, v))) <= 1e-4
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_second_derivative_through_logproba_chain(variant):
+    """ctc_loss_from_logproba differentiated twice (tests/test_hessian.py:110-147, test_classic_ctc_loss.py:443-477)."""
+    pkg = _pkg()
+    B, T, V, L = 2, 4, 3, 2
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=7)
+    data, lp = orc.ctc_loss_data(labels, logits, ll, tl, 0, variant)
+    logprobas = _cuda(lp, torch.float32).requires_grad_(True)
+    loss = pkg.ctc_loss_from_logproba(_cuda(labels), logprobas, _cuda(ll), _cuda(tl), 0, _cls(variant))
+    (g,) = torch.autograd.grad(loss.sum(), logprobas, create_graph=True)
+    assert np.max(np.abs(g.detach().cpu().numpy() - data.gradient)) <= GRAD_ATOL_SHORT
+    H = np.zeros((B, T, V, T, V))
+    for t in range(T):
+        for k in range(V):
+            (row,) = torch.autograd.grad(g[:, t, k].sum(), logprobas, retain_graph=True)
+            H[:, t, k] = row.cpu().numpy()
+    assert np.max(np.abs(H - data.hessian)) <= HESS_ATOL
+    with pytest.raises(NotImplementedError):
+        lp2 = _cuda(lp, torch.float32).requires_grad_(True)
+        loss2 = pkg.ctc_loss_from_logproba(_cuda(labels), lp2, _cuda(ll), _cuda(tl), 0, _cls(variant))
+        (g2,) = torch.autograd.grad(loss2.sum(), lp2, create_graph=True)
+        (h2,) = torch.autograd.grad(g2.sum(), lp2, create_graph=True)
+        torch.autograd.grad(h2.sum(), lp2)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs at full size: oracle on a subsample + size-independent properties
+# ------------------------------------------------------------------------------------------------------------------
+def _full_size_check(B, T, V, L, variant, ragged, n_check=4, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn((B, T, V), generator=g, dtype=torch.float32)
+    labels = torch.randint(1, V, (B, L), generator=g, dtype=torch.int32)
+    if ragged:
+        tl = torch.randint(T // 2, T + 1, (B,), generator=g, dtype=torch.int32)
+        ll = torch.randint(L // 2, L + 1, (B,), generator=g, dtype=torch.int32)
+    else:
+        tl = torch.full((B,), T, dtype=torch.int32)
+        ll = torch.full((B,), L, dtype=torch.int32)
+    x = logits.cuda().requires_grad_(True)
+    loss = _fn(variant)(labels.cuda(), x, ll.cuda(), tl.cuda(), 0, max_label_length=L)
+    loss.sum().backward()
+    grad = x.grad
+    # properties: every gradient row sums to zero (softmax - occupancy), padded rows are exactly zero
+    assert float(grad.sum(dim=2).abs().max()) < 2e-3
+    mask = torch.arange(T, device="cuda")[None, :] >= tl.cuda()[:, None]
+    assert float(grad[mask].abs().max() if mask.any() else 0.0) == 0.0
+    assert torch.isfinite(loss).all()
+    idx = np.linspace(0, B - 1, n_check).astype(int)
+    want_loss, want_grad, _ = orc.loss_and_grad_logits(labels.numpy()[idx], logits.numpy()[idx], ll.numpy()[idx],
+                                                        tl.numpy()[idx], 0, variant)
+    _loss_close(loss.detach().cpu().numpy()[idx], want_loss)
+    err = float(np.max(np.abs(grad.cpu().numpy()[idx] - want_grad)))
+    print(f"[full-size B={B} T={T} V={V} L={L} variant={variant} ragged={ragged}] grad max-abs err {err:.3e}")
+    assert err <= (GRAD_ATOL_LONG if T >= 500 else GRAD_ATOL_SHORT)
+
+
+def test_config1_character_asr_shape():
+    """BASELINE.json configs[1]: classic_ctc_loss B=32 T=500 V=29 L=100."""
+    _full_size_check(32, 500, 29, 100, CLASSIC, ragged=False)
+    _full_size_check(32, 500, 29, 100, CLASSIC, ragged=True, seed=1)
+
+
+@pytest.mark.parametrize("variant", [SIMPLIFIED, CLASSIC])
+def test_config2_north_star_shape(variant):
+    """BASELINE.json configs[2]: simple_ctc_loss B=256 T=1000 V=1024 L=200 (and the classic loss on the same shape)."""
+    _full_size_check(256, 1000, 1024, 200, variant, ragged=False, n_check=3)
+    _full_size_check(256, 1000, 1024, 200, variant, ragged=True, n_check=3, seed=1)
+
+
+def test_config3_hessian_shape():
+    """BASELINE.json configs[3]: ClassicCtcLossData.hessian B=64 T=50 V=32 L=15."""
+    B, T, V, L = 64, 50, 32, 15
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=4)
+    obj, _ = _data_obj((logits, labels, ll, tl), CLASSIC)
+    got = obj.hessian
+    assert list(got.shape) == [B, T, V, T, V]
+    assert float((got - got.permute(0, 3, 4, 1, 2)).abs().max()) <= 2e-6
+    idx = [0, 31, 63]
+    data, _ = orc.ctc_loss_data(labels[idx], logits[idx], ll[idx], tl[idx], 0, CLASSIC)
+    assert np.max(np.abs(got[idx].cpu().numpy() - data.hessian_fast())) <= HESS_ATOL
+
+
+def test_config4_large_vocab_slice():
+    """BASELINE.json configs[4] (B=2048 T=1600 V=5000 L=400) on a one-GPU slice of the batch, incl. the edge samples."""
+    B, T, V, L = 8, 1600, 5000, 400
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn((B, T, V), generator=g, dtype=torch.float32)
+    labels = torch.randint(1, V, (B, L), generator=g, dtype=torch.int32)
+    tl = torch.full((B,), T, dtype=torch.int32)
+    ll = torch.full((B,), L, dtype=torch.int32)
+    logits[0, :, 1:] = -float("inf")
+    ll[2], tl[2] = 400, 300
+    ll[3] = 0
+    tl[4] = 0
+    x = logits.cuda().requires_grad_(True)
+    loss = _pkg().classic_ctc_loss(labels.cuda(), x, ll.cuda(), tl.cuda(), 0)
+    torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)).sum().backward()
+    got_loss, grad = loss.detach().cpu().numpy(), x.grad.cpu().numpy()
+    assert np.isinf(got_loss[[0, 2, 4]]).all() and not np.isnan(grad).any()
+    idx = [1, 3, 5]
+    want_loss, want_grad, _ = orc.loss_and_grad_logits(labels.numpy()[idx], logits.numpy()[idx], ll.numpy()[idx],
+                                                        tl.numpy()[idx], 0, CLASSIC)
+    _loss_close(got_loss[idx], want_loss)
+    assert np.max(np.abs(grad[idx] - want_grad)) <= GRAD_ATOL_LONG
+    for b in (0, 2, 4):
+        assert np.array_equal(grad[b], np.zeros_like(grad[b]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# boundary behaviour
+# ------------------------------------------------------------------------------------------------------------------
+def test_no_cpu_fallback_and_size_limits():
+    from tf_seq2seq_losses_b200 import _lib
+    pkg = _pkg()
+    with pytest.raises(_lib.CtcB200Error):
+        pkg.classic_ctc_loss(torch.ones((1, 2), dtype=torch.int32), torch.zeros((1, 4, 3)), torch.tensor([2]),
+                             torch.tensor([4]), 0)
+    with pytest.raises(_lib.CtcB200Error):   # 600 label states > 512
+        pkg.classic_ctc_loss(torch.ones((1, 600), dtype=torch.int32).cuda(), torch.zeros((1, 700, 3)).cuda(),
+                             torch.tensor([599]).cuda(), torch.tensor([700]).cuda(), 0)
+    with pytest.raises(AssertionError):      # base_loss.py:129-138
+        pkg.classic_ctc_loss(torch.ones((2, 2), dtype=torch.int32).cuda(), torch.zeros((1, 4, 3)).cuda(),
+                             torch.tensor([2]).cuda(), torch.tensor([4]).cuda(), 0)
+
+
+def test_host_buffer_entry_point_matches_device_entry_point():
+    """ctcb200_host_loss_grad (pinned host buffers, sliced copies) == ctcb200_loss_grad on resident tensors."""
+    from tf_seq2seq_losses_b200 import _lib
+    B, T, V, L = 10, 40, 64, 12
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=9)
+    ctx = _lib.HostContext(B, T, V, L, 0, SIMPLIFIED, L + 1, device=0, num_slices=3)
+    pin = lambda a: torch.as_tensor(a).pin_memory()
+    loss_h = torch.empty((B,), dtype=torch.float32).pin_memory()
+    grad_h = torch.empty((B, T, V), dtype=torch.float32).pin_memory()
+    ctx.loss_grad(pin(logits), pin(labels), pin(ll), pin(tl), loss_h, grad_h)
+    desc = _lib.make_desc(_cuda(logits), _cuda(labels), 0, SIMPLIFIED, L + 1)
+    loss_d, grad_d, _ = _lib.loss_grad(desc, _cuda(logits), _cuda(labels), _cuda(ll), _cuda(tl))
+    torch.cuda.synchronize()
+    assert torch.equal(loss_h, loss_d.cpu()) and torch.equal(grad_h, grad_d.cpu())
+    ctx.close()

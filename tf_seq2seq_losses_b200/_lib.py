@@ -1,0 +1,215 @@
+"""ctypes binding of libctc_b200.so (C ABI declared in include/ctc_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, this module raises.  The CPU
+oracle under ``oracle/`` is test infrastructure and is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+CLASSIC = 0
+SIMPLIFIED = 1
+INPUT_LOGPROBAS = 1
+WS_LOSS_GRAD, WS_STATES, WS_HESSIAN = 0, 1, 2
+MAX_STATES = 512
+MAX_TOKENS = 32768
+
+_LIB_NAME = "libctc_b200.so"
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+EXPORTED_SYMBOLS = (
+    "ctcb200_version", "ctcb200_strerror", "ctcb200_stage_names", "ctcb200_launches_per_call",
+    "ctcb200_workspace_bytes", "ctcb200_loss_grad", "ctcb200_states",
+    "ctcb200_hessian", "ctcb200_hvp", "ctcb200_host_create", "ctcb200_host_loss_grad",
+    "ctcb200_host_grad_device_ptr", "ctcb200_host_destroy",
+)
+
+
+class Desc(ctypes.Structure):
+    """struct ctcb200_desc."""
+    _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("V", ctypes.c_int32), ("Lw", ctypes.c_int32),
+                ("blank", ctypes.c_int32), ("variant", ctypes.c_int32), ("U", ctypes.c_int32),
+                ("flags", ctypes.c_uint32)]
+
+
+class CtcB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Loads the shared library once; raises loudly when it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise CtcB200Error(
+            f"{_LIB_PATH} not found: build it with `make -C tf_seq2seq_losses_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, i32p, fp = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
+    dp = ctypes.POINTER(Desc)
+    lib.ctcb200_version.restype = ctypes.c_int
+    lib.ctcb200_strerror.restype = ctypes.c_char_p
+    lib.ctcb200_strerror.argtypes = [ctypes.c_int]
+    lib.ctcb200_stage_names.restype = ctypes.c_char_p
+    lib.ctcb200_launches_per_call.restype = ctypes.c_int
+    lib.ctcb200_launches_per_call.argtypes = [dp]
+    lib.ctcb200_workspace_bytes.restype = ctypes.c_size_t
+    lib.ctcb200_workspace_bytes.argtypes = [dp, ctypes.c_int]
+    lib.ctcb200_loss_grad.restype = ctypes.c_int
+    lib.ctcb200_loss_grad.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, fp, fp, vp, ctypes.c_size_t, vp]
+    lib.ctcb200_states.restype = ctypes.c_int
+    lib.ctcb200_states.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, fp, vp, ctypes.c_size_t, vp]
+    lib.ctcb200_hessian.restype = ctypes.c_int
+    lib.ctcb200_hessian.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, fp, vp, ctypes.c_size_t, vp]
+    lib.ctcb200_hvp.restype = ctypes.c_int
+    lib.ctcb200_hvp.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, vp, ctypes.c_size_t, vp]
+    lib.ctcb200_host_create.restype = ctypes.c_int
+    lib.ctcb200_host_create.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.ctcb200_host_loss_grad.restype = ctypes.c_int
+    lib.ctcb200_host_loss_grad.argtypes = [vp, fp, i32p, i32p, i32p, fp, fp]
+    lib.ctcb200_host_grad_device_ptr.restype = ctypes.c_void_p
+    lib.ctcb200_host_grad_device_ptr.argtypes = [vp]
+    lib.ctcb200_host_destroy.restype = None
+    lib.ctcb200_host_destroy.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise CtcB200Error(f"libctc_b200: {load().ctcb200_strerror(code).decode()} (code {code})")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise CtcB200Error(f"{name} must live on a CUDA device: libctc_b200 has no CPU path")
+
+
+def _workspace(desc: Desc, what: int, device: torch.device) -> torch.Tensor:
+    n = load().ctcb200_workspace_bytes(ctypes.byref(desc), what)
+    if n == 0 and desc.B > 0:
+        raise CtcB200Error("libctc_b200: descriptor rejected (unsupported size: more than "
+                           f"{MAX_STATES} label states or {MAX_TOKENS} tokens, or an invalid field)")
+    # torch's caching allocator returns 512-byte aligned blocks; the ABI needs 256
+    return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
+
+
+def make_desc(logits: torch.Tensor, labels: torch.Tensor, blank: int, variant: int, U: int, flags: int = 0) -> Desc:
+    B, T, V = logits.shape
+    return Desc(B, T, V, labels.shape[1], int(blank), int(variant), int(U), int(flags))
+
+
+def _stream(device: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def loss_grad(desc: Desc, logits, labels, label_length, logit_length, d_loss=None, want_grad_logits=True,
+              want_grad_logprobas=False, grad_logits_out=None):
+    """ctcb200_loss_grad on the current stream of ``logits.device``.  Returns (loss, grad_logits, grad_logprobas)."""
+    _require_cuda(logits, "logits")
+    dev = logits.device
+    loss = torch.empty((desc.B,), dtype=torch.float32, device=dev)
+    gl = None
+    if want_grad_logits:
+        gl = grad_logits_out if grad_logits_out is not None else torch.empty_like(logits)
+    gp = torch.empty_like(logits) if want_grad_logprobas else None
+    ws = _workspace(desc, WS_LOSS_GRAD, dev)
+    with torch.cuda.device(dev):
+        check(load().ctcb200_loss_grad(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
+                                       _ptr(logit_length), _ptr(d_loss), _ptr(loss), _ptr(gl), _ptr(gp),
+                                       _ptr(ws), ws.numel(), _stream(dev)))
+    return loss, gl, gp
+
+
+def states(desc: Desc, logits, labels, label_length, logit_length):
+    """ctcb200_states.  Returns (alpha, beta, loss) in the reference layouts."""
+    _require_cuda(logits, "logits")
+    dev = logits.device
+    shape = (desc.B, desc.T + 1, desc.U, 2) if desc.variant == CLASSIC else (desc.B, desc.T + 1, desc.U)
+    alpha = torch.empty(shape, dtype=torch.float32, device=dev)
+    beta = torch.empty(shape, dtype=torch.float32, device=dev)
+    loss = torch.empty((desc.B,), dtype=torch.float32, device=dev)
+    ws = _workspace(desc, WS_STATES, dev)
+    with torch.cuda.device(dev):
+        check(load().ctcb200_states(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
+                                    _ptr(logit_length), _ptr(alpha), _ptr(beta), _ptr(loss), _ptr(ws), ws.numel(),
+                                    _stream(dev)))
+    return alpha, beta, loss
+
+
+def hessian(desc: Desc, logits, labels, label_length, logit_length):
+    """ctcb200_hessian.  Returns (hessian [B,T,V,T,V], loss, grad_logprobas)."""
+    _require_cuda(logits, "logits")
+    dev = logits.device
+    B, T, V = desc.B, desc.T, desc.V
+    hess = torch.empty((B, T, V, T, V), dtype=torch.float32, device=dev)
+    loss = torch.empty((B,), dtype=torch.float32, device=dev)
+    g = torch.empty((B, T, V), dtype=torch.float32, device=dev)
+    ws = _workspace(desc, WS_HESSIAN, dev)
+    if B > 0 and T > 0:
+        with torch.cuda.device(dev):
+            check(load().ctcb200_hessian(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
+                                         _ptr(logit_length), _ptr(hess), _ptr(loss), _ptr(g), _ptr(ws), ws.numel(),
+                                         _stream(dev)))
+    return hess, loss, g
+
+
+def hvp(desc: Desc, logits, labels, label_length, logit_length, d_gradient):
+    """ctcb200_hvp: sum_{t',k'} d_gradient[b,t',k'] * hessian[b,t,k,t',k'] -> [B,T,V]."""
+    _require_cuda(logits, "logits")
+    dev = logits.device
+    out = torch.empty((desc.B, desc.T, desc.V), dtype=torch.float32, device=dev)
+    ws = _workspace(desc, WS_HESSIAN, dev)
+    if desc.B > 0 and desc.T > 0:
+        d_gradient = d_gradient.contiguous()
+        with torch.cuda.device(dev):
+            check(load().ctcb200_hvp(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
+                                     _ptr(logit_length), _ptr(d_gradient), _ptr(out), _ptr(ws), ws.numel(),
+                                     _stream(dev)))
+    return out
+
+
+class HostContext:
+    """ctcb200_host_*: loss + gradient from HOST buffers (pinned tensors), copies overlapped with the kernels."""
+
+    def __init__(self, B, T, V, Lw, blank, variant, U, device=0, num_slices=8):
+        self.desc = Desc(B, T, V, Lw, blank, variant, U, 0)
+        self.device = int(device)
+        handle = ctypes.c_void_p()
+        check(load().ctcb200_host_create(ctypes.byref(self.desc), self.device, int(num_slices), ctypes.byref(handle)))
+        self._h = handle
+
+    def loss_grad(self, logits, labels, label_length, logit_length, loss_out, grad_out=None):
+        for name, t in (("logits", logits), ("labels", labels), ("label_length", label_length),
+                        ("logit_length", logit_length), ("loss_out", loss_out)):
+            if t.is_cuda or not t.is_contiguous():
+                raise CtcB200Error(f"{name} must be a contiguous host tensor")
+        check(load().ctcb200_host_loss_grad(self._h, _ptr(logits), _ptr(labels), _ptr(label_length),
+                                            _ptr(logit_length), _ptr(loss_out), _ptr(grad_out)))
+        return loss_out
+
+    def grad_device_ptr(self) -> int:
+        return int(load().ctcb200_host_grad_device_ptr(self._h) or 0)
+
+    def close(self):
+        if self._h:
+            load().ctcb200_host_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

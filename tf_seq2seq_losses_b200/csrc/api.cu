@@ -1,0 +1,192 @@
+// C ABI of libctc_b200.so (include/ctc_b200.h): descriptor validation, workspace carving, kernel sequencing.
+#include <new>
+
+#include "common.cuh"
+
+namespace ctcb200 {
+
+static size_t align256(size_t n) { return (n + 255) & ~size_t(255); }
+
+static int make_problem(const ctcb200_desc* d, Problem* p) {
+  if (d == nullptr) return CTCB200_ERR_NULL_POINTER;
+  if (d->B < 0 || d->T < 0 || d->V < 1 || d->Lw < 0 || d->U < 0) return CTCB200_ERR_BAD_DESCRIPTOR;
+  if (d->blank < 0 || d->blank >= d->V) return CTCB200_ERR_BAD_DESCRIPTOR;
+  if (d->variant != CTCB200_CLASSIC && d->variant != CTCB200_SIMPLIFIED) return CTCB200_ERR_BAD_DESCRIPTOR;
+  if (d->flags & ~(CTCB200_INPUT_LOGPROBAS | CTCB200_STAGE_MASK)) return CTCB200_ERR_BAD_DESCRIPTOR;
+  p->B = d->B; p->T = d->T; p->V = d->V; p->Lw = d->Lw; p->blank = d->blank; p->variant = d->variant;
+  p->U = d->U > 0 ? d->U : d->Lw + 1;
+  p->NS = (p->U + kWarp - 1) / kWarp;
+  if (p->NS > kMaxNS || d->V > kMaxV) return CTCB200_ERR_UNSUPPORTED_SIZE;
+  if ((long long)d->B * (long long)(d->T + 1) > (1LL << 40)) return CTCB200_ERR_UNSUPPORTED_SIZE;
+  p->Upad = p->NS * kWarp;
+  p->S = d->variant == CTCB200_CLASSIC ? 2 : 1;
+  p->input_logprobas = (d->flags & CTCB200_INPUT_LOGPROBAS) != 0;
+  p->logits = nullptr; p->labels = nullptr; p->label_length = nullptr; p->logit_length = nullptr;
+  return CTCB200_OK;
+}
+
+struct Carve {
+  size_t off = 0;
+  size_t take(size_t bytes) { size_t o = off; off += align256(bytes); return o; }
+};
+
+static size_t carve(const Problem& p, int what, char* base, Scratch* s, float** grad_tmp) {
+  Carve c;
+  const size_t rows = (size_t)p.B * p.T, srows = (size_t)p.B * (p.T + 1) * p.S * p.Upad;
+  const size_t o_lse = c.take(rows * 4), o_h = c.take(rows * 4), o_d = c.take(rows * p.Upad * 4);
+  const size_t o_a = c.take(srows * 4), o_b = c.take(srows * 4), o_loss = c.take((size_t)p.B * 4);
+  const size_t o_ca = c.take((size_t)p.B * (p.T + 1) * 8), o_cb = c.take((size_t)p.B * (p.T + 1) * 8);
+  const size_t o_ld = c.take((size_t)p.B * 8);
+  size_t o_g = 0;
+  if (what == CTCB200_WS_HESSIAN) o_g = c.take(rows * p.V * 4);
+  if (base != nullptr) {
+    s->rowlse = reinterpret_cast<float*>(base + o_lse);
+    s->h = reinterpret_cast<float*>(base + o_h);
+    s->dT = reinterpret_cast<float*>(base + o_d);
+    s->alphaT = reinterpret_cast<float*>(base + o_a);
+    s->betaT = reinterpret_cast<float*>(base + o_b);
+    s->loss = reinterpret_cast<float*>(base + o_loss);
+    s->ca = reinterpret_cast<double*>(base + o_ca);
+    s->cb = reinterpret_cast<double*>(base + o_cb);
+    s->lossd = reinterpret_cast<double*>(base + o_ld);
+    if (grad_tmp) *grad_tmp = what == CTCB200_WS_HESSIAN ? reinterpret_cast<float*>(base + o_g) : nullptr;
+  }
+  return c.off;
+}
+
+static int check_common(const ctcb200_desc* desc, Problem* p, int what, const float* logits, const int32_t* labels,
+                        const int32_t* label_length, const int32_t* logit_length, void* ws, size_t ws_bytes,
+                        Scratch* s, float** grad_tmp) {
+  int rc = make_problem(desc, p);
+  if (rc != CTCB200_OK) return rc;
+  if (p->B > 0) {
+    if (label_length == nullptr || logit_length == nullptr) return CTCB200_ERR_NULL_POINTER;
+    if (p->T > 0 && logits == nullptr) return CTCB200_ERR_NULL_POINTER;
+    if (p->Lw > 0 && labels == nullptr) return CTCB200_ERR_NULL_POINTER;
+  }
+  const size_t need = carve(*p, what, nullptr, nullptr, nullptr);
+  if (need > 0 && p->B > 0) {
+    if (ws == nullptr) return CTCB200_ERR_NULL_POINTER;
+    if (reinterpret_cast<uintptr_t>(ws) & 255) return CTCB200_ERR_MISALIGNED;
+    if (ws_bytes < need) return CTCB200_ERR_WORKSPACE_TOO_SMALL;
+  }
+  carve(*p, what, static_cast<char*>(ws), s, grad_tmp);
+  p->logits = logits; p->labels = labels; p->label_length = label_length; p->logit_length = logit_length;
+  return CTCB200_OK;
+}
+
+#define CTCB200_CUDA(call)                       \
+  do {                                           \
+    if ((call) != cudaSuccess) {                 \
+      (void)cudaGetLastError();                  \
+      return CTCB200_ERR_CUDA;                   \
+    }                                            \
+  } while (0)
+
+}  // namespace ctcb200
+
+using namespace ctcb200;
+
+extern "C" {
+
+int ctcb200_version(void) { return CTCB200_VERSION; }
+
+const char* ctcb200_strerror(int code) {
+  switch (code) {
+    case CTCB200_OK: return "ok";
+    case CTCB200_ERR_NULL_POINTER: return "null pointer";
+    case CTCB200_ERR_BAD_DESCRIPTOR: return "bad descriptor";
+    case CTCB200_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case CTCB200_ERR_UNSUPPORTED_SIZE: return "unsupported size (U > 512 states or V > 32768 tokens)";
+    case CTCB200_ERR_CUDA: return "CUDA launch failure";
+    case CTCB200_ERR_MISALIGNED: return "workspace must be 256-byte aligned";
+    default: return "unknown error";
+  }
+}
+
+const char* ctcb200_stage_names(void) { return "k1_softmax_gather,k2_recursion,k3_grad"; }
+
+int ctcb200_launches_per_call(const ctcb200_desc* desc) {
+  Problem p;
+  if (make_problem(desc, &p) != CTCB200_OK || p.B == 0) return 0;
+  return (p.T > 0 ? 1 : 0) + 1 + (p.T > 0 ? 1 : 0);
+}
+
+size_t ctcb200_workspace_bytes(const ctcb200_desc* desc, int what) {
+  Problem p;
+  if (make_problem(desc, &p) != CTCB200_OK) return 0;
+  if (what < CTCB200_WS_LOSS_GRAD || what > CTCB200_WS_HESSIAN) return 0;
+  return carve(p, what, nullptr, nullptr, nullptr);
+}
+
+int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                      const int32_t* label_length, const int32_t* logit_length, const float* d_loss, float* loss,
+                      float* grad_logits, float* grad_logprobas, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  Problem p; Scratch s;
+  int rc = check_common(desc, &p, CTCB200_WS_LOSS_GRAD, logits, labels, label_length, logit_length, workspace,
+                        workspace_bytes, &s, nullptr);
+  if (rc != CTCB200_OK) return rc;
+  if (p.B == 0) return CTCB200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* loss_out = loss ? loss : s.loss;
+  const unsigned stages = (desc->flags & CTCB200_STAGE_MASK) >> CTCB200_STAGE_SHIFT;
+  if (stages == 0 || (stages & 1u)) CTCB200_CUDA(launch_softmax_gather(p, s, st));
+  if (stages == 0 || (stages & 2u)) CTCB200_CUDA(launch_recursion(p, s, loss_out, false, st));
+  if (stages == 0 || (stages & 4u)) CTCB200_CUDA(launch_grad(p, s, d_loss, grad_logits, grad_logprobas, st));
+  return CTCB200_OK;
+}
+
+int ctcb200_states(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                   const int32_t* label_length, const int32_t* logit_length, float* alpha, float* beta,
+                   float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  Problem p; Scratch s;
+  int rc = check_common(desc, &p, CTCB200_WS_STATES, logits, labels, label_length, logit_length, workspace,
+                        workspace_bytes, &s, nullptr);
+  if (rc != CTCB200_OK) return rc;
+  if (desc->U <= 0) return CTCB200_ERR_BAD_DESCRIPTOR;   // the output shape depends on the true U
+  if (p.B == 0) return CTCB200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CTCB200_CUDA(launch_softmax_gather(p, s, st));
+  CTCB200_CUDA(launch_recursion(p, s, loss ? loss : s.loss, true, st));
+  CTCB200_CUDA(launch_export_states(p, s, alpha, beta, st));
+  return CTCB200_OK;
+}
+
+int ctcb200_hessian(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                    const int32_t* label_length, const int32_t* logit_length, float* hessian, float* loss,
+                    float* grad_logprobas, void* workspace, size_t workspace_bytes, void* stream) {
+  Problem p; Scratch s; float* gtmp = nullptr;
+  int rc = check_common(desc, &p, CTCB200_WS_HESSIAN, logits, labels, label_length, logit_length, workspace,
+                        workspace_bytes, &s, &gtmp);
+  if (rc != CTCB200_OK) return rc;
+  if (p.B == 0 || p.T == 0) return CTCB200_OK;
+  if (hessian == nullptr) return CTCB200_ERR_NULL_POINTER;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* loss_out = loss ? loss : s.loss;
+  CTCB200_CUDA(launch_softmax_gather(p, s, st));
+  CTCB200_CUDA(launch_recursion(p, s, loss_out, false, st));
+  float* g = grad_logprobas ? grad_logprobas : gtmp;
+  CTCB200_CUDA(launch_grad(p, s, nullptr, nullptr, g, st));
+  CTCB200_CUDA(launch_hessian(p, s, g, hessian, nullptr, nullptr, st));
+  return CTCB200_OK;
+}
+
+int ctcb200_hvp(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                const int32_t* label_length, const int32_t* logit_length, const float* d_gradient, float* out,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  Problem p; Scratch s; float* gtmp = nullptr;
+  int rc = check_common(desc, &p, CTCB200_WS_HESSIAN, logits, labels, label_length, logit_length, workspace,
+                        workspace_bytes, &s, &gtmp);
+  if (rc != CTCB200_OK) return rc;
+  if (p.B == 0 || p.T == 0) return CTCB200_OK;
+  if (d_gradient == nullptr || out == nullptr) return CTCB200_ERR_NULL_POINTER;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CTCB200_CUDA(launch_softmax_gather(p, s, st));
+  CTCB200_CUDA(launch_recursion(p, s, s.loss, false, st));
+  CTCB200_CUDA(launch_grad(p, s, nullptr, nullptr, gtmp, st));
+  CTCB200_CUDA(launch_hessian(p, s, gtmp, nullptr, d_gradient, out, st));
+  return CTCB200_OK;
+}
+
+}  // extern "C"

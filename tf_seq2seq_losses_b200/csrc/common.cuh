@@ -1,0 +1,115 @@
+// Shared device helpers and the internal launch interface of libctc_b200.so (sm_100a).
+//
+// Notation follows the reference (tf_seq2seq_losses): B batch, T frames, V tokens, U = max label length + 1
+// "tokens emitted so far" states, h[t] = log-prob of blank at frame t, d[t,l] = log-prob of label token l at
+// frame t (-inf for l >= label_length).  See DESIGN.md for the data layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <cmath>
+#include <stdint.h>
+
+#include "../../include/ctc_b200.h"
+
+namespace ctcb200 {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxNS = 16;          // states per lane -> U <= 512
+constexpr int kMaxV = 32768;        // token -> slot map lives in shared memory as int16
+#define kNegInf (-INFINITY)
+
+// ---- numerics (tf_seq2seq_losses/tools.py:57-71) -------------------------------------------------------------
+// log(e^a + e^b); (-inf,-inf) -> -inf, a == b -> a + log 2, exactly as the reference's three-way tf.where.
+// MUFU.EX2 / MUFU.LG2 based (2 MUFU per call): abs error ~2^-21, inside the fp32 tolerance of the path.
+__device__ __forceinline__ float lse2(float a, float b) {
+  float m = fmaxf(a, b);
+  float n = fminf(a, b);
+  float e = __expf(n - m);                       // n - m <= 0; NaN only when m == -inf (handled below)
+  float r = m + __logf(1.0f + e);
+  return (m == kNegInf) ? kNegInf : r;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ---- private state layout -------------------------------------------------------------------------------------
+// A recursion warp keeps NS = ceil(U/32) consecutive states per lane: state l lives in lane l / NS, register
+// l % NS.  Scratch rows are stored "transposed" so that a warp-wide load of register j is one coalesced 128 B
+// line: position(l) = (l % NS) * 32 + l / NS, row pitch Upad = 32 * NS.
+__host__ __device__ __forceinline__ int state_pos(int l, int ns) { return (l % ns) * kWarp + l / ns; }
+
+// streaming (read-once / write-once) global accesses that do not pollute L1
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// ---- problem description shared by all launchers -------------------------------------------------------------
+struct Problem {
+  int B, T, V, Lw, blank, variant;
+  int U;      // state count bound (desc.U or Lw+1)
+  int NS;     // states per lane
+  int Upad;   // 32 * NS
+  int S;      // 1 simplified, 2 classic (closed/open)
+  bool input_logprobas;
+  const float* logits;
+  const int32_t* labels;
+  const int32_t* label_length;
+  const int32_t* logit_length;
+};
+
+struct Scratch {
+  float* rowlse;   // [B*T]      log-sum-exp of each logits row (0 when the input is log-probabilities)
+  float* h;        // [B*T]      blank log-prob
+  float* dT;       // [B*T*Upad] label-token log-probs, private layout
+  float* alphaT;   // [B*(T+1)*S*Upad]
+  float* betaT;    // [B*(T+1)*S*Upad]
+  float* loss;     // [B] (when the caller passes no loss buffer)
+  // Offset renormalisation: the stored rows are alpha[t,.] - ca[t] and beta[t,.] - cb[t]; the offsets are running
+  // sums of lagged warp maxima kept in double, so magnitudes stay O(10) instead of O(T log V) and the fp32
+  // rounding error of the path no longer grows with T.  lossd = -(alpha[T,L]) in double.
+  double* ca;      // [B*(T+1)]
+  double* cb;      // [B*(T+1)]
+  double* lossd;   // [B]
+};
+
+// per-utterance clamped lengths
+__device__ __forceinline__ int utt_label_len(const Problem& p, int b) {
+  int L = p.label_length[b];
+  return max(0, min(L, p.U - 1));
+}
+__device__ __forceinline__ int utt_frames(const Problem& p, int b) {
+  int n = p.logit_length[b];
+  return max(0, min(n, p.T));
+}
+// the reference's cleaned label (base_loss.py:395-418): labels beyond Lw or label_length are blank
+__device__ __forceinline__ int utt_token(const Problem& p, int b, int l, int L) {
+  return (l >= 0 && l < L && l < p.Lw) ? p.labels[(size_t)b * p.Lw + l] : p.blank;
+}
+
+cudaError_t launch_softmax_gather(const Problem& p, const Scratch& s, cudaStream_t st);
+cudaError_t launch_recursion(const Problem& p, const Scratch& s, float* loss, bool full_states, cudaStream_t st);
+cudaError_t launch_grad(const Problem& p, const Scratch& s, const float* d_loss, float* grad_logits,
+                        float* grad_logprobas, cudaStream_t st);
+cudaError_t launch_export_states(const Problem& p, const Scratch& s, float* alpha, float* beta, cudaStream_t st);
+cudaError_t launch_hessian(const Problem& p, const Scratch& s, const float* g, float* hessian,
+                           const float* d_gradient, float* hvp_out, cudaStream_t st);
+
+}  // namespace ctcb200

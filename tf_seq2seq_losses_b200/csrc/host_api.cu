@@ -1,0 +1,112 @@
+// Host-buffer entry points of libctc_b200.so (include/ctc_b200.h): the call a host without device tensors makes.
+// The batch is cut into slices; slice i's host->device copies, kernels and device->host copies are enqueued on
+// stream i % 2, so the PCIe copies of one slice overlap the kernels of the other.
+#include <new>
+
+#include "common.cuh"
+
+struct ctcb200_host_ctx {
+  ctcb200_desc desc;
+  int device;
+  int num_slices;
+  cudaStream_t streams[2];
+  float* d_logits;
+  float* d_grad;
+  int32_t* d_labels;
+  int32_t* d_label_length;
+  int32_t* d_logit_length;
+  float* d_loss;
+  void* ws[2];
+  size_t ws_bytes;
+};
+
+extern "C" {
+
+void ctcb200_host_destroy(ctcb200_host_ctx* c) {
+  if (c == nullptr) return;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < 2; ++i) {
+    if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    if (c->ws[i]) cudaFree(c->ws[i]);
+  }
+  cudaFree(c->d_logits); cudaFree(c->d_grad); cudaFree(c->d_labels); cudaFree(c->d_label_length);
+  cudaFree(c->d_logit_length); cudaFree(c->d_loss);
+  delete c;
+}
+
+int ctcb200_host_create(const ctcb200_desc* desc, int device, int num_slices, ctcb200_host_ctx** out) {
+  if (desc == nullptr || out == nullptr) return CTCB200_ERR_NULL_POINTER;
+  *out = nullptr;
+  if (num_slices < 1) num_slices = 1;
+  if (desc->B > 0 && num_slices > desc->B) num_slices = desc->B;
+  const int slice_b = desc->B > 0 ? (desc->B + num_slices - 1) / num_slices : 0;
+  ctcb200_desc sd = *desc;
+  sd.B = slice_b;
+  const size_t ws_bytes = ctcb200_workspace_bytes(&sd, CTCB200_WS_LOSS_GRAD);
+  if (ws_bytes == 0 && slice_b > 0) return CTCB200_ERR_BAD_DESCRIPTOR;
+  ctcb200_host_ctx* c = new (std::nothrow) ctcb200_host_ctx();
+  if (c == nullptr) return CTCB200_ERR_CUDA;
+  c->desc = *desc; c->device = device; c->num_slices = num_slices; c->ws_bytes = ws_bytes;
+  const size_t n = (size_t)desc->B * desc->T * desc->V;
+  bool ok = cudaSetDevice(device) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i) {
+    ok = ok && cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->ws[i], ws_bytes ? ws_bytes : 256) == cudaSuccess;
+  }
+  ok = ok && cudaMalloc(&c->d_logits, n ? n * 4 : 256) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_grad, n ? n * 4 : 256) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_labels, (size_t)desc->B * desc->Lw * 4 + 256) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_label_length, (size_t)desc->B * 4 + 256) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_logit_length, (size_t)desc->B * 4 + 256) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_loss, (size_t)desc->B * 4 + 256) == cudaSuccess;
+  if (!ok) {
+    (void)cudaGetLastError();
+    ctcb200_host_destroy(c);
+    return CTCB200_ERR_CUDA;
+  }
+  *out = c;
+  return CTCB200_OK;
+}
+
+float* ctcb200_host_grad_device_ptr(ctcb200_host_ctx* c) { return c ? c->d_grad : nullptr; }
+
+int ctcb200_host_loss_grad(ctcb200_host_ctx* c, const float* host_logits, const int32_t* host_labels,
+                           const int32_t* host_label_length, const int32_t* host_logit_length, float* host_loss,
+                           float* host_grad_logits) {
+  if (c == nullptr) return CTCB200_ERR_NULL_POINTER;
+  const ctcb200_desc& d = c->desc;
+  if (d.B == 0) return CTCB200_OK;
+  if (host_label_length == nullptr || host_logit_length == nullptr || host_loss == nullptr ||
+      (d.T > 0 && host_logits == nullptr) || (d.Lw > 0 && host_labels == nullptr))
+    return CTCB200_ERR_NULL_POINTER;
+  if (cudaSetDevice(c->device) != cudaSuccess) return CTCB200_ERR_CUDA;
+  const int slice_b = (d.B + c->num_slices - 1) / c->num_slices;
+  const size_t tv = (size_t)d.T * d.V;
+  int rc = CTCB200_OK;
+  for (int i = 0, b0 = 0; b0 < d.B; ++i, b0 += slice_b) {
+    const int nb = (d.B - b0 < slice_b) ? d.B - b0 : slice_b;
+    cudaStream_t st = c->streams[i & 1];
+    ctcb200_desc sd = d;
+    sd.B = nb;
+    bool ok = true;
+    if (tv) ok = ok && cudaMemcpyAsync(c->d_logits + b0 * tv, host_logits + b0 * tv, nb * tv * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (d.Lw) ok = ok && cudaMemcpyAsync(c->d_labels + (size_t)b0 * d.Lw, host_labels + (size_t)b0 * d.Lw, (size_t)nb * d.Lw * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->d_label_length + b0, host_label_length + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->d_logit_length + b0, host_logit_length + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (!ok) { rc = CTCB200_ERR_CUDA; break; }
+    rc = ctcb200_loss_grad(&sd, c->d_logits + b0 * tv, c->d_labels + (size_t)b0 * d.Lw, c->d_label_length + b0,
+                           c->d_logit_length + b0, nullptr, c->d_loss + b0, c->d_grad + b0 * tv, nullptr,
+                           c->ws[i & 1], c->ws_bytes, st);
+    if (rc != CTCB200_OK) break;
+    ok = cudaMemcpyAsync(host_loss + b0, c->d_loss + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (host_grad_logits && tv)
+      ok = ok && cudaMemcpyAsync(host_grad_logits + b0 * tv, c->d_grad + b0 * tv, nb * tv * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (!ok) { rc = CTCB200_ERR_CUDA; break; }
+  }
+  for (int i = 0; i < 2; ++i)
+    if (cudaStreamSynchronize(c->streams[i]) != cudaSuccess) rc = CTCB200_ERR_CUDA;
+  if (rc == CTCB200_ERR_CUDA) (void)cudaGetLastError();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// Per-frame transition occupancies: the device form of _combine_transition_probabilities
+// (tf_seq2seq_losses/classic_ctc_loss.py:565-669, simplified_ctc_loss.py:456-534) followed by exp(loss + .).
+// Shared by the gradient writer (K3) and the Hessian kernel (K4).
+#pragma once
+#include "common.cuh"
+
+namespace ctcb200 {
+
+constexpr unsigned short kNoSlot = 0xFFFFu;
+
+// online log-sum-exp accumulator (per lane), merged across the warp at the end
+struct LseAcc {
+  float m = kNegInf, s = 0.0f;
+  __device__ __forceinline__ void add(float v) {
+    if (v == kNegInf) return;
+    if (v > m) {
+      s = s * __expf(m - v) + 1.0f;     // m == -inf -> s == 0 and exp(-inf) == 0
+      m = v;
+    } else {
+      s += __expf(v - m);
+    }
+  }
+  __device__ __forceinline__ float warp_result() const {
+    const float M = warp_max(m);
+    const float part = (m == kNegInf) ? 0.0f : s * __expf(m - M);
+    const float tot = warp_sum(part);
+    return (M == kNegInf) ? kNegInf : M + __logf(tot);
+  }
+};
+
+// neighbours of a private-layout position (state l+1 / l-1); -1 when outside the 32*NS states
+__device__ __forceinline__ int pos_next(int pos, int lane, int ns) {
+  return ((pos >> 5) + 1 < ns) ? pos + kWarp : ((lane < 31) ? lane + 1 : -1);
+}
+__device__ __forceinline__ int pos_prev(int pos, int lane, int ns) {
+  return ((pos >> 5) > 0) ? pos - kWarp : ((lane > 0) ? (ns - 1) * kWarp + lane - 1 : -1);
+}
+
+// Shared-memory tables of one utterance, built once per CTA:
+//   toks[l]  cleaned label (base_loss.py:395-418), l in [0, Upad): blank for l >= label_length
+//   map[k]   token -> slot (first label position carrying k); blank -> slot Upad; kNoSlot for tokens not in the label
+__device__ __forceinline__ void build_utterance_tables(const Problem& p, int b, int L, int* toks,
+                                                       unsigned short* map, int Vpad) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int k = tid; k < Vpad; k += nthr) map[k] = kNoSlot;
+  for (int l = tid; l < p.Upad; l += nthr) toks[l] = utt_token(p, b, l, L);
+  __syncthreads();
+  for (int l = tid; l < L; l += nthr) {
+    const int tok = toks[l];
+    if (tok < 0 || tok >= p.V) continue;
+    unsigned short old = map[tok];
+    while (old > (unsigned short)l) {                    // 16-bit atomic min via CAS
+      const unsigned short assumed = old;
+      old = atomicCAS(&map[tok], assumed, (unsigned short)l);
+      if (old == assumed) break;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) map[p.blank] = (unsigned short)p.Upad;   // the blank column is overridden (blank_mask tf.where)
+  __syncthreads();
+}
+
+__device__ __forceinline__ int tok_at(const Problem& p, const int* toks, int l) {
+  return (l >= 0 && l < p.Upad) ? toks[l] : p.blank;
+}
+
+// One warp, one frame.  A: state log-weights before the frame, Bn: state log-weights after it, both in the private
+// layout with pitch Upad between the closed / open planes; d: label-token log-probs of the frame; h: blank log-prob.
+// Fills acc[slot] = sum over the transitions emitting that slot's token of exp(lossb + A + emission + Bn) for every
+// slot (acc[Upad] = blank) and returns the total over all tokens.  acc must hold Upad + 1 floats.
+template <bool CLASSIC>
+__device__ __forceinline__ float row_occupancies(const Problem& p, int L, int lane, const float* A, const float* Bn,
+                                                 const float* d, float h, float lossb, const int* toks,
+                                                 const unsigned short* map, float* acc) {
+  for (int i = lane; i <= p.Upad; i += kWarp) acc[i] = 0.0f;
+  __syncwarp();
+  LseAcc blank_acc;
+  float occ_sum = 0.0f;
+  for (int pos = lane; pos < p.Upad; pos += kWarp) {
+    const int l = lane * p.NS + (pos >> 5);
+    if (l > L) continue;
+    const int pn = pos_next(pos, lane, p.NS), pp = pos_prev(pos, lane, p.NS);
+    const int tok = toks[l];
+    const unsigned short slot = (tok >= 0 && tok < p.V) ? map[tok] : kNoSlot;
+    if (!CLASSIC) {
+      const float a = A[pos];
+      blank_acc.add(a + Bn[pos]);
+      if (l < L) {
+        const float bnext = (pn >= 0) ? Bn[pn] : kNegInf;
+        const float o = __expf(lossb + (a + d[pos] + bnext));
+        if (slot != kNoSlot && o > 0.0f) atomicAdd(&acc[slot], o);
+        occ_sum += (slot != kNoSlot && slot != p.Upad) ? o : 0.0f;
+      }
+    } else {
+      const float a0 = A[pos], a1 = A[p.Upad + pos];
+      blank_acc.add(lse2(a0, a1) + Bn[pos]);
+      const int tok_prev = tok_at(p, toks, l - 1);
+      if (l < L) {     // diagonal step emitting label[l]: any state of l -> open state of l+1
+        const float bnext = (pn >= 0) ? Bn[p.Upad + pn] : kNegInf;
+        const float dv = d[pos];
+        const float v1 = (tok == tok_prev) ? kNegInf : a1 + dv;
+        const float o = __expf(lossb + (lse2(a0 + dv, v1) + bnext));
+        if (slot != kNoSlot && o > 0.0f) atomicAdd(&acc[slot], o);
+        occ_sum += (slot != kNoSlot && slot != p.Upad) ? o : 0.0f;
+      }
+      if (l >= 1 && pp >= 0) {   // horizontal step re-emitting label[l-1]: open l -> open l
+        const unsigned short sp = (tok_prev >= 0 && tok_prev < p.V) ? map[tok_prev] : kNoSlot;
+        const float o = __expf(lossb + (a1 + d[pp] + Bn[p.Upad + pos]));
+        if (sp != kNoSlot && o > 0.0f) atomicAdd(&acc[sp], o);
+        occ_sum += (sp != kNoSlot && sp != p.Upad) ? o : 0.0f;
+      }
+    }
+  }
+  const float occ_blank = __expf(lossb + (h + blank_acc.warp_result()));
+  occ_sum = warp_sum(occ_sum) + occ_blank;
+  __syncwarp();
+  if (lane == 0) acc[p.Upad] = occ_blank;
+  __syncwarp();
+  return occ_sum;
+}
+
+}  // namespace ctcb200
