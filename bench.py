@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default=None, choices=["simplified", "classic"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--staged", action="store_true", help="force the three staged kernels instead of the fused one")
     ap.add_argument("--ragged", action="store_true", help="logit_length~U[T/2,T], label_length~U[L/2,L]")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
@@ -194,7 +195,7 @@ def main():
         local_B, global_B = b1 - b0, B
     logits_h, labels_h, ll_h, tl_h = synth(local_B, T, V, L, 1000 + rank, args.ragged)
     logits, labels, ll, tl = logits_h.to(dev), labels_h.to(dev), ll_h.to(dev), tl_h.to(dev)
-    desc = _lib.make_desc(logits, labels, 0, vid, L + 1)
+    desc = _lib.make_desc(logits, labels, 0, vid, L + 1, _lib.FORCE_STAGED if args.staged else 0)
     lib = _lib.load()
     ws = torch.empty(max(lib.ctcb200_workspace_bytes(ctypes.byref(desc), _lib.WS_LOSS_GRAD), 256), dtype=torch.uint8, device=dev)
     loss = torch.empty((local_B,), dtype=torch.float32, device=dev)
@@ -233,7 +234,7 @@ def main():
     launches_per_step = int(lib.ctcb200_launches_per_call(ctypes.byref(desc))) if hasattr(lib, "ctcb200_launches_per_call") else 3
     stage_ms = {}
     if hasattr(lib, "ctcb200_stage_names"):
-        names = lib.ctcb200_stage_names().decode().split(",")
+        names = lib.ctcb200_stage_names(ctypes.byref(desc)).decode().split(",")
         for i, name in enumerate(names):
             d = _lib.Desc(desc.B, desc.T, desc.V, desc.Lw, desc.blank, desc.variant, desc.U, desc.flags | ((1 << i) << 8))
             for _ in range(3):

@@ -39,6 +39,9 @@ extern "C" {
                                       base_loss.py:71-99, and the data-class constructors, base_loss.py:105-114):
                                       the log-softmax of tools.py:27-40 is skipped */
 
+#define CTCB200_FORCE_STAGED 2u    /* ctcb200_loss_grad: use the three staged kernels (K1 softmax+gather, K2 recursion,
+                                      K3 gradient) even where the fused single-launch kernel applies */
+
 /* Profiling aid: flags bits 8..15 select which stages of ctcb200_loss_grad are enqueued (bit 8+i = i-th name of
  * ctcb200_stage_names()); 0 = all.  A partial call must follow a full call on the same workspace and inputs. */
 #define CTCB200_STAGE_SHIFT 8
@@ -73,8 +76,9 @@ typedef struct ctcb200_desc {
 int ctcb200_version(void);
 const char* ctcb200_strerror(int code);
 
-/* Comma-separated stage (kernel) names of ctcb200_loss_grad, and the number of kernels one full call enqueues. */
-const char* ctcb200_stage_names(void);
+/* Comma-separated stage (kernel) names ctcb200_loss_grad runs for this descriptor (the fused kernel is a single
+ * stage), and the number of kernels one full call enqueues. */
+const char* ctcb200_stage_names(const ctcb200_desc* desc);
 int ctcb200_launches_per_call(const ctcb200_desc* desc);
 
 /* Bytes of device workspace needed by the entry point named by `what` (CTCB200_WS_*); 0 on a bad descriptor. */

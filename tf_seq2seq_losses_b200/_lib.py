@@ -14,6 +14,7 @@ import torch
 CLASSIC = 0
 SIMPLIFIED = 1
 INPUT_LOGPROBAS = 1
+FORCE_STAGED = 2
 WS_LOSS_GRAD, WS_STATES, WS_HESSIAN = 0, 1, 2
 MAX_STATES = 512
 MAX_TOKENS = 32768
@@ -59,6 +60,7 @@ def load() -> ctypes.CDLL:
     lib.ctcb200_strerror.restype = ctypes.c_char_p
     lib.ctcb200_strerror.argtypes = [ctypes.c_int]
     lib.ctcb200_stage_names.restype = ctypes.c_char_p
+    lib.ctcb200_stage_names.argtypes = [dp]
     lib.ctcb200_launches_per_call.restype = ctypes.c_int
     lib.ctcb200_launches_per_call.argtypes = [dp]
     lib.ctcb200_workspace_bytes.restype = ctypes.c_size_t
@@ -106,9 +108,14 @@ def _workspace(desc: Desc, what: int, device: torch.device) -> torch.Tensor:
     return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
 
 
+# Flags OR-ed into every descriptor built by make_desc.  Tests set this to FORCE_STAGED to exercise the three staged
+# kernels on shapes the fused kernel would otherwise take (also settable with CTCB200_FORCE_STAGED=1).
+DEFAULT_FLAGS = FORCE_STAGED if os.environ.get("CTCB200_FORCE_STAGED", "0") == "1" else 0
+
+
 def make_desc(logits: torch.Tensor, labels: torch.Tensor, blank: int, variant: int, U: int, flags: int = 0) -> Desc:
     B, T, V = logits.shape
-    return Desc(B, T, V, labels.shape[1], int(blank), int(variant), int(U), int(flags))
+    return Desc(B, T, V, labels.shape[1], int(blank), int(variant), int(U), int(flags) | DEFAULT_FLAGS)
 
 
 def _stream(device: torch.device):

@@ -12,7 +12,7 @@ static int make_problem(const ctcb200_desc* d, Problem* p) {
   if (d->B < 0 || d->T < 0 || d->V < 1 || d->Lw < 0 || d->U < 0) return CTCB200_ERR_BAD_DESCRIPTOR;
   if (d->blank < 0 || d->blank >= d->V) return CTCB200_ERR_BAD_DESCRIPTOR;
   if (d->variant != CTCB200_CLASSIC && d->variant != CTCB200_SIMPLIFIED) return CTCB200_ERR_BAD_DESCRIPTOR;
-  if (d->flags & ~(CTCB200_INPUT_LOGPROBAS | CTCB200_STAGE_MASK)) return CTCB200_ERR_BAD_DESCRIPTOR;
+  if (d->flags & ~(CTCB200_INPUT_LOGPROBAS | CTCB200_FORCE_STAGED | CTCB200_STAGE_MASK)) return CTCB200_ERR_BAD_DESCRIPTOR;
   p->B = d->B; p->T = d->T; p->V = d->V; p->Lw = d->Lw; p->blank = d->blank; p->variant = d->variant;
   p->U = d->U > 0 ? d->U : d->Lw + 1;
   p->NS = (p->U + kWarp - 1) / kWarp;
@@ -104,11 +104,23 @@ const char* ctcb200_strerror(int code) {
   }
 }
 
-const char* ctcb200_stage_names(void) { return "k1_softmax_gather,k2_recursion,k3_grad"; }
+// The fused kernel takes the loss+gradient call whenever the shape allows (V % 4 == 0 for the 16-byte TMA rows and the
+// shared-memory plan fits); pointer alignment is checked per call.
+static int fused_workers(const ctcb200_desc* desc, const Problem& p) {
+  if (desc->flags & CTCB200_FORCE_STAGED) return 0;
+  return fused_pick_workers(p);
+}
+
+const char* ctcb200_stage_names(const ctcb200_desc* desc) {
+  Problem p;
+  if (make_problem(desc, &p) == CTCB200_OK && fused_workers(desc, p) > 0) return "kf_fused";
+  return "k1_softmax_gather,k2_recursion,k3_grad";
+}
 
 int ctcb200_launches_per_call(const ctcb200_desc* desc) {
   Problem p;
   if (make_problem(desc, &p) != CTCB200_OK || p.B == 0) return 0;
+  if (fused_workers(desc, p) > 0) return 1;
   return (p.T > 0 ? 1 : 0) + 1 + (p.T > 0 ? 1 : 0);
 }
 
@@ -130,6 +142,12 @@ int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32
   if (p.B == 0) return CTCB200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* loss_out = loss ? loss : s.loss;
+  const int W = fused_workers(desc, p);
+  if (W > 0 && grad_logits != nullptr && grad_logprobas == nullptr && p.T > 0 &&
+      ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(grad_logits)) & 15) == 0) {
+    CTCB200_CUDA(launch_fused(p, s, d_loss, loss_out, grad_logits, W, st));
+    return CTCB200_OK;
+  }
   const unsigned stages = (desc->flags & CTCB200_STAGE_MASK) >> CTCB200_STAGE_SHIFT;
   if (stages == 0 || (stages & 1u)) CTCB200_CUDA(launch_softmax_gather(p, s, st));
   if (stages == 0 || (stages & 2u)) CTCB200_CUDA(launch_recursion(p, s, loss_out, false, st));

@@ -20,14 +20,22 @@ constexpr int kMaxV = 32768;        // token -> slot map lives in shared memory 
 #define kNegInf (-INFINITY)
 
 // ---- numerics (tf_seq2seq_losses/tools.py:57-71) -------------------------------------------------------------
-// log(e^a + e^b); (-inf,-inf) -> -inf, a == b -> a + log 2, exactly as the reference's three-way tf.where.
-// MUFU.EX2 / MUFU.LG2 based (2 MUFU per call): abs error ~2^-21, inside the fp32 tolerance of the path.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// log(e^a + e^b) = max + log1p(exp(-|a-b|)); (-inf,-inf) -> -inf and a == b -> a + log 2, exactly as the reference's
+// three-way tf.where.  2 MUFU (EX2, LG2) + 6 ALU ops, no branches: for a == b == -inf the difference is NaN, which
+// fminf(NaN, 0) turns into 0, and -inf + log 2 is -inf again.  Abs error ~2^-21, inside the fp32 tolerance of the path.
 __device__ __forceinline__ float lse2(float a, float b) {
-  float m = fmaxf(a, b);
-  float n = fminf(a, b);
-  float e = __expf(n - m);                       // n - m <= 0; NaN only when m == -inf (handled below)
-  float r = m + __logf(1.0f + e);
-  return (m == kNegInf) ? kNegInf : r;
+  const float t = fminf(-fabsf(a - b) * 1.4426950408889634f, 0.0f);
+  return fmaf(lg2_approx(1.0f + ex2_approx(t)), 0.6931471805599453f, fmaxf(a, b));
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -108,6 +116,9 @@ cudaError_t launch_softmax_gather(const Problem& p, const Scratch& s, cudaStream
 cudaError_t launch_recursion(const Problem& p, const Scratch& s, float* loss, bool full_states, cudaStream_t st);
 cudaError_t launch_grad(const Problem& p, const Scratch& s, const float* d_loss, float* grad_logits,
                         float* grad_logprobas, cudaStream_t st);
+int fused_pick_workers(const Problem& p);
+cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss, float* loss, float* grad, int W,
+                         cudaStream_t st);
 cudaError_t launch_export_states(const Problem& p, const Scratch& s, float* alpha, float* beta, cudaStream_t st);
 cudaError_t launch_hessian(const Problem& p, const Scratch& s, const float* g, float* hessian,
                            const float* d_gradient, float* hvp_out, cudaStream_t st);

@@ -5,7 +5,7 @@
 //   classic:    _alpha_step classic_ctc_loss.py:415-451, beta_step :349-364, loss :152-165
 // One warp per (utterance, direction): alpha and beta run concurrently as independent CTAs.  The state vector
 // lives in registers, NS consecutive states per lane; the l-1 / l+1 neighbour crosses lanes with one shuffle per
-// step; the per-frame inputs (h[t], d[t,.]) are prefetched kPrefetch frames ahead with coalesced loads.
+// step; the per-frame inputs (h[t], d[t,.]) stream through a kStages-deep cp.async shared-memory ring.
 //
 // Classic transition algebra (s=0 closed, s=1 open; rep[l] = label[l]==label[l-1]; r[l] = d[l-1] when label[l-1]
 // is not the blank):
@@ -15,145 +15,51 @@
 //   B'[l,1] = lse(rep[l] ? h + B[l,0] : B'[l,0], r[l] + B[l,1])
 // which is the reference's [next,prev] table form (classic_ctc_loss.py:464-563) with the -inf entries removed.
 #include "common.cuh"
+#include "recursion.cuh"
 
 namespace ctcb200 {
 
-constexpr int kPrefetch = 4;
+constexpr int kGroup = 4;      // frames per unrolled group (the renormalisation cadence)
+constexpr int kStages = 16;    // cp.async ring depth: frames in flight per warp (DRAM latency / step time)
 
-template <int NS>
-struct FrameQueue {
-  float d[kPrefetch][NS];
-  float h[kPrefetch];
-};
-
-template <int NS>
-__device__ __forceinline__ void load_frame(const Problem& p, const Scratch& s, long long row, int lane, float* d,
-                                           float& h) {
-  const float* src = s.dT + (size_t)row * p.Upad + lane;
-#pragma unroll
-  for (int j = 0; j < NS; ++j) d[j] = __ldg(src + j * kWarp);
-  h = __ldg(s.h + row);
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// per-lane static label facts for the classic variant
+// Ring slot = one frame: Upad label-token log-probs (private layout) followed by h.  Always commits a group (an
+// empty one when there is nothing left to fetch) so that wait_group counts stay uniform.  Upad = 32 * NS is a
+// compile-time constant, so the copy is a fixed, predicated sequence of 16-byte cp.async with no loop.
 template <int NS>
-struct LabelBits {
-  unsigned rep;    // bit j: label[l] == label[l-1]        (l = lane*NS + j; label[-1] := blank)
-  unsigned nb;     // bit j: label[l] != blank
-  bool rep_left;   // rep / nb of state lane*NS - 1 (lives in lane-1)
-  bool nb_left;
-};
-
-template <int NS>
-__device__ __forceinline__ LabelBits<NS> make_label_bits(const Problem& p, int b, int L, int lane) {
-  LabelBits<NS> lb;
-  lb.rep = 0u;
-  lb.nb = 0u;
+__device__ __forceinline__ void issue_frame(const float* d_src, const float* h_src, float* ring, int slot, bool valid,
+                                            int lane) {
+  constexpr int kUpad = NS * kWarp, kChunks = kUpad / 4;
+  if (valid) {
+    float* dst = ring + slot * (kUpad + 4);
 #pragma unroll
-  for (int j = 0; j < NS; ++j) {
-    const int l = lane * NS + j;
-    const int tok = utt_token(p, b, l, L);
-    const int prev = utt_token(p, b, l - 1, L);
-    if (tok == prev) lb.rep |= 1u << j;
-    if (tok != p.blank) lb.nb |= 1u << j;
+    for (int k = 0; k < (kChunks + kWarp - 1) / kWarp; ++k) {
+      const int c = k * kWarp + lane;
+      if (c < kChunks) cp_async16(dst + 4 * c, d_src + 4 * c);
+    }
+    if (lane == 0) cp_async4(dst + kUpad, h_src);
   }
-  const unsigned rl = __shfl_up_sync(kFull, lb.rep, 1), nl = __shfl_up_sync(kFull, lb.nb, 1);
-  lb.rep_left = lane > 0 && ((rl >> (NS - 1)) & 1u);
-  lb.nb_left = lane > 0 && ((nl >> (NS - 1)) & 1u);
-  return lb;
-}
-
-// ---- one frame of each recursion ------------------------------------------------------------------------------
-template <int NS>
-__device__ __forceinline__ void alpha_step_simplified(float* a, const float* d, float h, int lane) {
-  float carry = __shfl_up_sync(kFull, d[NS - 1] + a[NS - 1], 1);
-  if (lane == 0) carry = kNegInf;
-#pragma unroll
-  for (int j = NS - 1; j >= 1; --j) a[j] = lse2(h + a[j], d[j - 1] + a[j - 1]);
-  a[0] = lse2(h + a[0], carry);
+  cp_async_commit();
 }
 
 template <int NS>
-__device__ __forceinline__ void beta_step_simplified(float* bt, const float* d, float h, int lane) {
-  float carry = __shfl_down_sync(kFull, bt[0], 1);
-  if (lane == 31) carry = kNegInf;
+__device__ __forceinline__ void read_frame(const float* ring, int slot, int lane, float* d, float& h) {
+  constexpr int kUpad = NS * kWarp;
+  const float* src = ring + slot * (kUpad + 4);
 #pragma unroll
-  for (int j = 0; j < NS - 1; ++j) bt[j] = lse2(h + bt[j], d[j] + bt[j + 1]);
-  bt[NS - 1] = lse2(h + bt[NS - 1], d[NS - 1] + carry);
-}
-
-template <int NS>
-__device__ __forceinline__ void alpha_step_classic(float* a0, float* a1, const float* d, float h, int lane,
-                                                   const LabelBits<NS>& lb) {
-  // d of the left neighbour's top state: pure data, off the dependency chain
-  float d_left = __shfl_up_sync(kFull, d[NS - 1], 1);
-  if (lane == 0) d_left = kNegInf;
-  float S[NS];
-#pragma unroll
-  for (int j = NS - 1; j >= 0; --j) S[j] = lse2(a0[j], a1[j]);
-  const float x_top = ((lb.rep >> (NS - 1)) & 1u) ? a0[NS - 1] : S[NS - 1];
-  float x_left = __shfl_up_sync(kFull, x_top, 1);
-  if (lane == 0) x_left = kNegInf;
-#pragma unroll
-  for (int j = NS - 1; j >= 1; --j) {
-    const float x = ((lb.rep >> (j - 1)) & 1u) ? a0[j - 1] : S[j - 1];
-    const float r = ((lb.nb >> (j - 1)) & 1u) ? d[j - 1] : kNegInf;
-    a1[j] = lse2(r + a1[j], d[j - 1] + x);
-  }
-  {
-    const float r = lb.nb_left ? d_left : kNegInf;
-    a1[0] = lse2(r + a1[0], d_left + x_left);
-  }
-#pragma unroll
-  for (int j = 0; j < NS; ++j) a0[j] = h + S[j];
-}
-
-template <int NS>
-__device__ __forceinline__ void beta_step_classic(float* b0, float* b1, const float* d, float h, int lane,
-                                                  const LabelBits<NS>& lb) {
-  float d_left = __shfl_up_sync(kFull, d[NS - 1], 1);
-  if (lane == 0) d_left = kNegInf;
-  float carry = __shfl_down_sync(kFull, b1[0], 1);
-  if (lane == 31) carry = kNegInf;
-#pragma unroll
-  for (int j = 0; j < NS; ++j) {
-    const float nxt = (j < NS - 1) ? b1[j + 1] : carry;      // old B[l+1,1]
-    const float stay = h + b0[j];
-    const float n0 = lse2(stay, d[j] + nxt);
-    const float dl = (j > 0) ? d[j - 1] : d_left;
-    const bool nbl = (j > 0) ? ((lb.nb >> (j - 1)) & 1u) : lb.nb_left;
-    const float r = nbl ? dl : kNegInf;
-    const float base = ((lb.rep >> j) & 1u) ? stay : n0;
-    b1[j] = lse2(base, r + b1[j]);                            // uses old b1[j]; b1[j+1] already consumed above
-    b0[j] = n0;
-  }
-}
-
-// Offset renormalisation (see Scratch in common.cuh).  The warp maximum is taken right after frame k == 0 of every
-// kPrefetch-frame group and subtracted two frames later, so its five dependent shuffles overlap the next frames'
-// arithmetic instead of lengthening the serial chain.
-template <int NS, bool CLASSIC>
-__device__ __forceinline__ float state_max(const float* v0, const float* v1) {
-  float m = kNegInf;
-#pragma unroll
-  for (int j = 0; j < NS; ++j) m = fmaxf(m, CLASSIC ? fmaxf(v0[j], v1[j]) : v0[j]);
-  return warp_max(m);
-}
-template <int NS, bool CLASSIC>
-__device__ __forceinline__ void apply_offset(float* v0, float* v1, float m, double& c) {
-  if (m == kNegInf) return;              // nothing reachable: leave the -inf vector alone
-#pragma unroll
-  for (int j = 0; j < NS; ++j) {
-    v0[j] -= m;
-    if (CLASSIC) v1[j] -= m;
-  }
-  c += (double)m;
-}
-
-template <int NS>
-__device__ __forceinline__ void store_row(float* dst, const float* v, int lane) {
-#pragma unroll
-  for (int j = 0; j < NS; ++j) dst[j * kWarp + lane] = v[j];
+  for (int j = 0; j < NS; ++j) d[j] = src[j * kWarp + lane];
+  h = src[kUpad];
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------
@@ -168,7 +74,7 @@ __global__ void __launch_bounds__(kWarp) k2_recursion(Problem p, Scratch s, floa
   const long long frame0 = (long long)b * p.T;
   LabelBits<NS> lb;
   if (CLASSIC) lb = make_label_bits<NS>(p, b, L, lane);
-  FrameQueue<NS> q;
+  extern __shared__ __align__(16) float ring[];
 
   if (blockIdx.y == 0) {
     // ------------------------------------------------ alpha: t = 0 .. n_t-1 ----------------------------------
@@ -186,20 +92,21 @@ __global__ void __launch_bounds__(kWarp) k2_recursion(Problem p, Scratch s, floa
     if (CLASSIC) store_row<NS>(out + p.Upad, a1, lane);
     if (lane == 0) offs[0] = 0.0;
     const int n_run = full_states ? p.T : n_t;
+    const float* dsrc = s.dT + (size_t)frame0 * p.Upad;
+    const float* hsrc = s.h + frame0;
+    for (int k = 0; k < kStages - 1; ++k) issue_frame<NS>(dsrc + (size_t)k * (NS * kWarp), hsrc + k, ring, k, k < n_t, lane);
+    for (int t0 = 0; t0 < n_run; t0 += kGroup) {
 #pragma unroll
-    for (int k = 0; k < kPrefetch; ++k)
-      if (k < n_t) load_frame<NS>(p, s, frame0 + k, lane, q.d[k], q.h[k]);
-    for (int t0 = 0; t0 < n_run; t0 += kPrefetch) {
-#pragma unroll
-      for (int k = 0; k < kPrefetch; ++k) {
+      for (int k = 0; k < kGroup; ++k) {
         const int t = t0 + k;
         if (t < n_run) {
           float d[NS], h;
           if (t < n_t) {
-#pragma unroll
-            for (int j = 0; j < NS; ++j) d[j] = q.d[k][j];
-            h = q.h[k];
-            if (t + kPrefetch < n_t) load_frame<NS>(p, s, frame0 + t + kPrefetch, lane, q.d[k], q.h[k]);
+            cp_async_wait<kStages - 2>();     // frame t has landed
+            __syncwarp();
+            read_frame<NS>(ring, t % kStages, lane, d, h);
+            const int nf = t + kStages - 1;   // refill the slot consumed one frame ago
+            issue_frame<NS>(dsrc + (size_t)nf * (NS * kWarp), hsrc + nf, ring, nf % kStages, nf < n_t, lane);
           } else {   // padded frame: blank with probability one (base_loss.py:378-393)
 #pragma unroll
             for (int j = 0; j < NS; ++j) d[j] = kNegInf;
@@ -245,19 +152,25 @@ __global__ void __launch_bounds__(kWarp) k2_recursion(Problem p, Scratch s, floa
       if (lane == 0) offs[t] = 0.0;
     }
     const int t_lo = full_states ? 0 : 1;                  // beta[0] is not needed by the gradient
+    // i-th processed frame is n_t-1-i; it lives in ring slot i % kStages
+    const float* dsrc = s.dT + (size_t)frame0 * p.Upad;
+    const float* hsrc = s.h + frame0;
+    for (int k = 0; k < kStages - 1; ++k) {
+      const int f = n_t - 1 - k;
+      issue_frame<NS>(dsrc + (ptrdiff_t)f * (NS * kWarp), hsrc + f, ring, k, f >= t_lo, lane);
+    }
+    for (int t0 = n_t - 1; t0 >= t_lo; t0 -= kGroup) {
 #pragma unroll
-    for (int k = 0; k < kPrefetch; ++k)
-      if (n_t - 1 - k >= t_lo) load_frame<NS>(p, s, frame0 + n_t - 1 - k, lane, q.d[k], q.h[k]);
-    for (int t0 = n_t - 1; t0 >= t_lo; t0 -= kPrefetch) {
-#pragma unroll
-      for (int k = 0; k < kPrefetch; ++k) {
+      for (int k = 0; k < kGroup; ++k) {
         const int t = t0 - k;
         if (t >= t_lo) {
           float d[NS], h;
-#pragma unroll
-          for (int j = 0; j < NS; ++j) d[j] = q.d[k][j];
-          h = q.h[k];
-          if (t - kPrefetch >= t_lo) load_frame<NS>(p, s, frame0 + t - kPrefetch, lane, q.d[k], q.h[k]);
+          const int i = n_t - 1 - t;
+          cp_async_wait<kStages - 2>();
+          __syncwarp();
+          read_frame<NS>(ring, i % kStages, lane, d, h);
+          const int ni = i + kStages - 1, nf = n_t - 1 - ni;
+          issue_frame<NS>(dsrc + (ptrdiff_t)nf * (NS * kWarp), hsrc + nf, ring, ni % kStages, nf >= t_lo, lane);
           if (CLASSIC) beta_step_classic<NS>(b0, b1, d, h, lane, lb);
           else beta_step_simplified<NS>(b0, d, h, lane);
           if (k == 0) m_pend = state_max<NS, CLASSIC>(b0, b1);
@@ -275,8 +188,9 @@ __global__ void __launch_bounds__(kWarp) k2_recursion(Problem p, Scratch s, floa
 template <int NS>
 static cudaError_t launch_ns(const Problem& p, const Scratch& s, float* loss, bool full, cudaStream_t st) {
   dim3 grid(p.B, 2);
-  if (p.variant == CTCB200_CLASSIC) k2_recursion<NS, true><<<grid, kWarp, 0, st>>>(p, s, loss, full);
-  else k2_recursion<NS, false><<<grid, kWarp, 0, st>>>(p, s, loss, full);
+  const size_t smem = (size_t)kStages * (p.Upad + 4) * sizeof(float);     // <= 33 KB
+  if (p.variant == CTCB200_CLASSIC) k2_recursion<NS, true><<<grid, kWarp, smem, st>>>(p, s, loss, full);
+  else k2_recursion<NS, false><<<grid, kWarp, smem, st>>>(p, s, loss, full);
   return cudaGetLastError();
 }
 

@@ -80,23 +80,36 @@ __global__ void __launch_bounds__(kK3Warps * kWarp)
     if (vec) {
       const float4* x4 = reinterpret_cast<const float4*>(x);
       const ushort4* m4 = reinterpret_cast<const ushort4*>(map);
-      for (int i = lane; i < (p.V >> 2); i += kWarp) {
-        const ushort4 m = m4[i];
-        float4 o;
-        o.x = (m.x != kNoSlot) ? acc[m.x] : 0.0f;
-        o.y = (m.y != kNoSlot) ? acc[m.y] : 0.0f;
-        o.z = (m.z != kNoSlot) ? acc[m.z] : 0.0f;
-        o.w = (m.w != kNoSlot) ? acc[m.w] : 0.0f;
-        if (gl) {
-          const float4 v = ldg_stream4(x4 + i);
-          float4 g;
-          g.x = scale * __expf(v.x - lse_row) - dl * o.x;
-          g.y = scale * __expf(v.y - lse_row) - dl * o.y;
-          g.z = scale * __expf(v.z - lse_row) - dl * o.z;
-          g.w = scale * __expf(v.w - lse_row) - dl * o.w;
-          stg_stream4(reinterpret_cast<float4*>(gl) + i, g);
+      const int n4 = p.V >> 2;
+      // kUnroll independent 128-bit loads are issued before any of them is consumed (memory-level parallelism)
+      constexpr int kUnroll = 4;
+      for (int i0 = 0; i0 < n4; i0 += kUnroll * kWarp) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int i = i0 + u * kWarp + lane;
+          if (gl && i < n4) v[u] = ldg_stream4(x4 + i);
         }
-        if (gp) stg_stream4(reinterpret_cast<float4*>(gp) + i, make_float4(-dl * o.x, -dl * o.y, -dl * o.z, -dl * o.w));
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int i = i0 + u * kWarp + lane;
+          if (i >= n4) continue;
+          const ushort4 m = m4[i];
+          float4 o;
+          o.x = (m.x != kNoSlot) ? acc[m.x] : 0.0f;
+          o.y = (m.y != kNoSlot) ? acc[m.y] : 0.0f;
+          o.z = (m.z != kNoSlot) ? acc[m.z] : 0.0f;
+          o.w = (m.w != kNoSlot) ? acc[m.w] : 0.0f;
+          if (gl) {
+            float4 g;
+            g.x = scale * __expf(v[u].x - lse_row) - dl * o.x;
+            g.y = scale * __expf(v[u].y - lse_row) - dl * o.y;
+            g.z = scale * __expf(v[u].z - lse_row) - dl * o.z;
+            g.w = scale * __expf(v[u].w - lse_row) - dl * o.w;
+            stg_stream4(reinterpret_cast<float4*>(gl) + i, g);
+          }
+          if (gp) stg_stream4(reinterpret_cast<float4*>(gp) + i, make_float4(-dl * o.x, -dl * o.y, -dl * o.z, -dl * o.w));
+        }
       }
     } else {
       for (int k = lane; k < p.V; k += kWarp) {

@@ -1,0 +1,514 @@
+// KF: the fused loss + d/dlogits kernel -- ONE launch for the whole hot path, one CTA per utterance.
+//
+// What it replaces in the reference: the log-softmax (tf_seq2seq_losses/tools.py:27-40), the label-state gathers
+// (base_loss.py:328-418), the alpha/beta tf.while_loop recursions (classic_ctc_loss.py:310-462,
+// simplified_ctc_loss.py:291-438), the loss read-out, _combine_transition_probabilities with its token scatter
+// (classic_ctc_loss.py:565-669, simplified_ctc_loss.py:456-534, base_loss.py:420-468), the gradient
+// (base_loss.py:262-298) and TF's autodiff of the log-softmax -- i.e. everything the staged kernels K1+K2+K3 do, with
+// the [B,T,U] gathered-probability scratch and one of the two state tensors never leaving the SM.
+//
+// Schedule ("meet in the middle").  For an utterance with n frames, M = n/2:
+//   phase A  alpha runs forward over frames 0..M-1 while beta runs backward over frames n-1..M.  Each side stores the
+//            state it held *before* consuming a frame (alpha[t] for t < M, beta[t+1] for t >= M) to global scratch.
+//   middle   logZ = logsumexp_l(alpha[M,l] + beta[M,l]) -- the normaliser every occupancy needs -- is known half-way.
+//   phase B  alpha continues over frames M..n-1 and beta over M-1..0.  At frame t the running side's state and the
+//            other side's stored state give the occupancies of that frame, and the gradient row is written at once.
+// Every logits row is therefore read twice (once per phase) and every gradient row written once; the serial chain is
+// n/2 + n/2 steps instead of 2n.
+//
+// Warp roles (per side s in {alpha, beta}; W row workers per side):
+//   recursion warp   NS states per lane in registers, one shuffle per frame (recursion.cuh); consumes per-frame
+//                    inputs (h, d[.]) from a shared-memory ring and publishes its pre-step state.
+//   row workers      each owns whole logits rows: a 1-D TMA bulk copy (cp.async.bulk + mbarrier complete_tx) lands the
+//                    row in shared memory (double buffered), the warp reduces it (phase A: row log-sum-exp), gathers
+//                    the <= U label columns into the ring, and in phase B combines alpha*beta into per-token
+//                    occupancies (occupancy.cuh) and streams out the dense gradient row with 128-bit stores.
+// Warps hand work to each other through monotonic counters in shared memory (st.release / ld.acquire at CTA scope);
+// there is no CTA-wide barrier inside a phase.
+#include "common.cuh"
+#include "occupancy.cuh"
+#include "recursion.cuh"
+
+namespace ctcb200 {
+
+constexpr int kRowSlots = 2;        // TMA row buffers per worker (current + prefetch)
+constexpr int kFusedGroup = 4;      // frames per unrolled group (renormalisation cadence, see recursion.cuh)
+constexpr int kMaxWorkers = 3;
+
+// ---- PTX helpers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D TMA: global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until(const unsigned* p, unsigned need) {
+  while (ld_acquire(p) < need) {
+  }
+}
+__device__ __forceinline__ void fused_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fused_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fused_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- shared-memory layout (one definition for host sizing and device carving) ---------------------------------------
+struct FusedLayout {
+  int W, R;                 // workers per side, ring depth (= 2W, a multiple of W)
+  int off_map, off_toks, off_xch, off_xoff, off_side0, total;
+  // offsets inside a side block
+  int s_ctl, s_bar, s_row, s_ringd, s_ringh, s_rings, s_ringc, s_stbuf, s_acc, side_bytes;
+};
+
+__host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W) {
+  FusedLayout f;
+  f.W = W;
+  f.R = 2 * W;
+  int o = 0;
+  f.off_map = o;  o += fl_align(((V + 7) & ~7) * 2, 16);
+  f.off_toks = o; o += Upad * 4;
+  f.off_xch = o;  o += 2 * S * Upad * 4;
+  f.off_xoff = o; o += 2 * 8;
+  o = fl_align(o, 128);
+  int s = 0;
+  f.s_ctl = s;   s += fl_align((2 * W + 2) * 4, 16);          // dcount[W], done[W], ccount, scount
+  f.s_bar = s;   s += W * kRowSlots * 8;
+  s = fl_align(s, 128);
+  f.s_row = s;   s += W * kRowSlots * V * 4;
+  f.s_ringd = s; s += f.R * Upad * 4;
+  f.s_ringh = s; s += fl_align(f.R * 4, 16);
+  f.s_rings = s; s += f.R * S * Upad * 4;
+  f.s_ringc = s; s += f.R * 8;
+  s = fl_align(s, 16);
+  f.s_stbuf = s; s += W * S * Upad * 4;
+  f.s_acc = s;   s += W * (Upad + kWarp) * 4;
+  f.side_bytes = fl_align(s, 128);
+  f.off_side0 = o;
+  f.total = o + 2 * f.side_bytes;
+  return f;
+}
+
+struct FusedArgs {
+  Problem p;
+  float* rowlse;        // [B*T]          row log-sum-exp (phase A -> phase B)
+  float* stateT;        // [B*T*S*Upad]   row t: alpha[t] if t < M(b) else beta[t+1]; private layout
+  double* coff;         // [B*T]          renormalisation offset of that row
+  const float* d_loss;  // [B] or null
+  float* loss;          // [B]
+  float* grad;          // [B,T,V]
+  int W;
+};
+
+// view of one side's shared memory
+struct SideView {
+  unsigned* dcount;   // [W] rows whose ring inputs each worker has published
+  unsigned* done;     // [W] rows each worker has completely finished (phase B)
+  unsigned* ccount;   // frames the recursion warp has consumed
+  unsigned* scount;   // frames whose pre-step state the recursion warp has published (phase B)
+  unsigned long long* bar;   // [W][kRowSlots]
+  float* row;         // [W][kRowSlots][V]
+  float* ringd;       // [R][Upad]
+  float* ringh;       // [R]
+  float* rings;       // [R][S*Upad]
+  double* ringc;      // [R]
+  float* stbuf;       // [W][S*Upad]
+  float* acc;         // [W][Upad+32]
+};
+
+__device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLayout& f, int side) {
+  unsigned char* base = smem + f.off_side0 + side * f.side_bytes;
+  SideView v;
+  unsigned* ctl = reinterpret_cast<unsigned*>(base + f.s_ctl);
+  v.dcount = ctl;
+  v.done = ctl + f.W;
+  v.ccount = ctl + 2 * f.W;
+  v.scount = ctl + 2 * f.W + 1;
+  v.bar = reinterpret_cast<unsigned long long*>(base + f.s_bar);
+  v.row = reinterpret_cast<float*>(base + f.s_row);
+  v.ringd = reinterpret_cast<float*>(base + f.s_ringd);
+  v.ringh = reinterpret_cast<float*>(base + f.s_ringh);
+  v.rings = reinterpret_cast<float*>(base + f.s_rings);
+  v.ringc = reinterpret_cast<double*>(base + f.s_ringc);
+  v.stbuf = reinterpret_cast<float*>(base + f.s_stbuf);
+  v.acc = reinterpret_cast<float*>(base + f.s_acc);
+  return v;
+}
+
+__device__ __forceinline__ void fused_zero_row(float* dst, int V, int lane) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = lane; i < (V >> 2); i += kWarp) stg_stream4(d4 + i, z);
+}
+
+// ---- recursion warp, one phase ---------------------------------------------------------------------------------------
+// Frame i of the phase is frame t = t_first + i * t_step of the utterance.  SIDE 0 = alpha (forward), 1 = beta.
+template <int NS, bool CLASSIC, int SIDE, bool PHASE_B>
+__device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int b, int count,
+                                          int t_first, int t_step, float* v0, float* v1, double& c,
+                                          const LabelBits<NS>& lb, int lane) {
+  constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
+  const int W = f.W, R = f.R;
+  float m_pend = kNegInf;
+  int w = 0, n = 0;            // worker / row of frame i
+  int slot = 0;                // i % R
+  int wj = 0, nj = 0;          // worker / row of frame i - R (phase B back-pressure)
+  float* g_state = a.stateT + ((size_t)b * a.p.T + t_first) * (size_t)(S * kUpad);
+  double* g_off = a.coff + (size_t)b * a.p.T + t_first;
+  const ptrdiff_t g_step = (ptrdiff_t)t_step * (S * kUpad);
+  for (int i0 = 0; i0 < count; i0 += kFusedGroup) {
+#pragma unroll
+    for (int k = 0; k < kFusedGroup; ++k) {
+      const int i = i0 + k;
+      if (i < count) {
+        spin_until(sv.dcount + w, (unsigned)(n + 1));          // the frame's inputs are in the ring
+        float d[NS];
+        const float* dsrc = sv.ringd + slot * kUpad;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) d[j] = dsrc[j * kWarp + lane];
+        const float h = sv.ringh[slot];
+        if (!PHASE_B) {
+          __syncwarp();
+          if (lane == 0) st_release(sv.ccount, (unsigned)(i + 1));   // ring slot may be refilled
+          // pre-step state -> global scratch for the other side's phase B
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+            g_state[j * kWarp + lane] = v0[j];
+            if (CLASSIC) g_state[kUpad + j * kWarp + lane] = v1[j];
+          }
+          if (lane == 0) *g_off = c;
+          g_state += g_step;
+          g_off += t_step;
+        } else {
+          if (i >= R) {                                          // the state slot's previous frame is fully processed
+            spin_until(sv.done + wj, (unsigned)(nj + 1));
+            if (++wj == W) { wj = 0; ++nj; }
+          }
+          float* dst = sv.rings + slot * (S * kUpad);
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+            dst[j * kWarp + lane] = v0[j];
+            if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
+          }
+          if (lane == 0) sv.ringc[slot] = c;
+          __syncwarp();
+          if (lane == 0) st_release(sv.scount, (unsigned)(i + 1));
+        }
+        if (SIDE == 0) {
+          if (CLASSIC) alpha_step_classic<NS>(v0, v1, d, h, lane, lb);
+          else alpha_step_simplified<NS>(v0, d, h, lane);
+        } else {
+          if (CLASSIC) beta_step_classic<NS>(v0, v1, d, h, lane, lb);
+          else beta_step_simplified<NS>(v0, d, h, lane);
+        }
+        if (k == 0) m_pend = state_max<NS, CLASSIC>(v0, v1);
+        if (k == 2) apply_offset<NS, CLASSIC>(v0, v1, m_pend, c);
+        if (++w == W) { w = 0; ++n; }
+        if (++slot == R) slot = 0;
+      }
+    }
+  }
+}
+
+// ---- row worker, one phase -------------------------------------------------------------------------------------------
+template <int NS, bool CLASSIC, int SIDE, bool PHASE_B>
+__device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int b, int w,
+                                             int count, int t_first, int t_step, int L, double lossd_mid, float dl,
+                                             const int* toks, const unsigned short* map, int lane) {
+  constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
+  const Problem& p = a.p;
+  const int W = f.W, R = f.R, V = p.V, n4 = V >> 2;
+  const int n_my = (count > w) ? (count - w + W - 1) / W : 0;
+  const unsigned row_bytes = (unsigned)V * 4u;
+  const float* logits_b = p.logits + (size_t)b * p.T * V;
+  float* rowbuf = sv.row + (size_t)w * kRowSlots * V;
+  unsigned long long* bars = sv.bar + w * kRowSlots;
+  float* stb = sv.stbuf + w * (S * kUpad);
+  float* acc = sv.acc + w * (kUpad + kWarp);
+
+  if (n_my > 0 && lane == 0) {
+    const int t = t_first + w * t_step;
+    mbar_expect_tx(bars + 0, row_bytes);
+    bulk_load(rowbuf, logits_b + (size_t)t * V, row_bytes, bars + 0);
+  }
+  int slot = w % R;    // ring slot of frame i = w + n*W
+  for (int n = 0; n < n_my; ++n) {
+    const int i = w + n * W;
+    const int t = t_first + i * t_step;
+    const int rs = n & 1;
+    // prefetch the next row into the other buffer (its previous occupant was finished in the last iteration)
+    if (n + 1 < n_my && lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(bars + (rs ^ 1), row_bytes);
+      bulk_load(rowbuf + (size_t)(rs ^ 1) * V, logits_b + (size_t)(t + W * t_step) * V, row_bytes, bars + (rs ^ 1));
+    }
+    float lse = 0.0f;
+    double cst = 0.0;
+    if (PHASE_B) {
+      // the other side's stored state for this frame: async copy now, consumed after the recursion catches up
+      const float* src = a.stateT + ((size_t)b * p.T + t) * (size_t)(S * kUpad);
+#pragma unroll
+      for (int k = 0; k < (S * kUpad / 4 + kWarp - 1) / kWarp; ++k) {
+        const int cidx = k * kWarp + lane;
+        if (cidx < S * kUpad / 4) fused_cp_async16(stb + 4 * cidx, src + 4 * cidx);
+      }
+      fused_cp_async_commit();
+      if (!p.input_logprobas) lse = a.rowlse[(size_t)b * p.T + t];   // written in phase A by this CTA: plain (coherent) load
+      cst = a.coff[(size_t)b * p.T + t];
+    }
+    mbar_wait(bars + rs, (unsigned)((n >> 1) & 1));            // the row has landed
+    const float* row = rowbuf + (size_t)rs * V;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+
+    // ---- stage 1: row statistics (phase A) and the gather of the label columns ----
+    if (!PHASE_B && !p.input_logprobas) {
+      float m = kNegInf;
+      for (int c4 = lane; c4 < n4; c4 += kWarp) {
+        const float4 v = row4[c4];
+        m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+      }
+      m = warp_max(m);
+      const float m0 = (m == kNegInf || m == INFINITY) ? 0.0f : m;   // tf.reduce_logsumexp convention
+      float sum = 0.0f;
+      for (int c4 = lane; c4 < n4; c4 += kWarp) {
+        const float4 v = row4[c4];
+        sum += (__expf(v.x - m0) + __expf(v.y - m0)) + (__expf(v.z - m0) + __expf(v.w - m0));
+      }
+      sum = warp_sum(sum);
+      lse = m0 + logf(sum);
+      if (lane == 0) a.rowlse[(size_t)b * p.T + t] = lse;
+    }
+    if (!PHASE_B && i >= R) spin_until(sv.ccount, (unsigned)(i - R + 1));   // ring slot consumed by the recursion
+    {
+      float* dd = sv.ringd + slot * kUpad;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int l = lane * NS + j;
+        float v = kNegInf;
+        if (l < L) {
+          const int tok = toks[l];
+          if (tok >= 0 && tok < V) v = row[tok] - lse;
+        }
+        dd[j * kWarp + lane] = v;
+      }
+      if (lane == 0) sv.ringh[slot] = row[p.blank] - lse;
+    }
+    __syncwarp();
+    if (lane == 0) st_release(sv.dcount + w, (unsigned)(n + 1));
+
+    // ---- stage 2 (phase B): occupancies of the frame and the dense gradient row ----
+    if (PHASE_B) {
+      spin_until(sv.scount, (unsigned)(i + 1));                 // the running side's state for this frame is published
+      fused_cp_async_wait_all();
+      __syncwarp();
+      const float* ring_state = sv.rings + slot * (S * kUpad);
+      const float lossb = (float)(lossd_mid + sv.ringc[slot] + cst);
+      const float* A = (SIDE == 0) ? ring_state : stb;         // alpha[t]
+      const float* Bn = (SIDE == 0) ? stb : ring_state;        // beta[t+1]
+      const float occ_sum =
+          row_occupancies<CLASSIC>(p, L, lane, A, Bn, sv.ringd + slot * kUpad, sv.ringh[slot], lossb, toks, map, acc);
+      const float scale = dl * occ_sum;
+      float4* out4 = reinterpret_cast<float4*>(a.grad + ((size_t)b * p.T + t) * V);
+      const ushort4* m4 = reinterpret_cast<const ushort4*>(map);
+#pragma unroll 4
+      for (int c4 = lane; c4 < n4; c4 += kWarp) {
+        const float4 v = row4[c4];
+        const ushort4 m = m4[c4];
+        float4 g;
+        g.x = scale * __expf(v.x - lse) - ((m.x != kNoSlot) ? dl * acc[m.x] : 0.0f);
+        g.y = scale * __expf(v.y - lse) - ((m.y != kNoSlot) ? dl * acc[m.y] : 0.0f);
+        g.z = scale * __expf(v.z - lse) - ((m.z != kNoSlot) ? dl * acc[m.z] : 0.0f);
+        g.w = scale * __expf(v.w - lse) - ((m.w != kNoSlot) ? dl * acc[m.w] : 0.0f);
+        stg_stream4(out4 + c4, g);
+      }
+      __syncwarp();
+      if (lane == 0) st_release(sv.done + w, (unsigned)(n + 1));
+    }
+    slot += W;
+    if (slot >= R) slot -= R;
+  }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------------------
+template <int NS, bool CLASSIC>
+__global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
+  const Problem& p = a.p;
+  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W);
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = f.W;
+  const int side = warp / (W + 1), role = warp % (W + 1);      // role 0 = recursion warp, 1..W = row workers
+  const int L = utt_label_len(p, b), n_t = utt_frames(p, b), M = n_t >> 1;
+  const float dl = a.d_loss ? a.d_loss[b] : 1.0f;
+
+  unsigned short* map = reinterpret_cast<unsigned short*>(smem + f.off_map);
+  int* toks = reinterpret_cast<int*>(smem + f.off_toks);
+  float* xch = reinterpret_cast<float*>(smem + f.off_xch);
+  double* xoff = reinterpret_cast<double*>(smem + f.off_xoff);
+  const SideView sv = side_view(smem, f, side);
+
+  auto reset_sync_state = [&]() {     // one thread: counters to zero, mbarriers to phase 0
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const SideView v = side_view(smem, f, s2);
+      for (int k = 0; k < 2 * W + 2; ++k) v.dcount[k] = 0u;
+      for (int k = 0; k < W * kRowSlots; ++k) mbar_init(v.bar + k, 1u);
+    }
+    fence_mbar_init();
+  };
+
+  build_utterance_tables(p, b, L, toks, map, (p.V + 7) & ~7);   // ends with __syncthreads
+  if (tid == 0) reset_sync_state();
+  __syncthreads();
+
+  // recursion state (only meaningful in the two recursion warps)
+  float v0[NS], v1[NS];
+  double c = 0.0;
+  LabelBits<NS> lb;
+  if (CLASSIC) lb = make_label_bits<NS>(p, b, L, lane);
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int l = lane * NS + j;
+    if (side == 0) {            // alpha[0] = log one_hot(state 0, closed)
+      v0[j] = (l == 0) ? 0.0f : kNegInf;
+      v1[j] = kNegInf;
+    } else {                    // beta[n_t] = log one_hot(label_length), both states
+      v0[j] = (l == L) ? 0.0f : kNegInf;
+      v1[j] = v0[j];
+    }
+  }
+
+  // ------------------------------------------------ phase A ------------------------------------------------------------
+  if (side == 0) {
+    if (role == 0) rec_phase<NS, CLASSIC, 0, false>(a, f, sv, b, M, 0, +1, v0, v1, c, lb, lane);
+    else worker_phase<NS, CLASSIC, 0, false>(a, f, sv, b, role - 1, M, 0, +1, L, 0.0, dl, toks, map, lane);
+  } else {
+    if (role == 0) rec_phase<NS, CLASSIC, 1, false>(a, f, sv, b, n_t - M, n_t - 1, -1, v0, v1, c, lb, lane);
+    else worker_phase<NS, CLASSIC, 1, false>(a, f, sv, b, role - 1, n_t - M, n_t - 1, -1, L, 0.0, dl, toks, map, lane);
+  }
+
+  // ------------------------------------------------ the middle ---------------------------------------------------------
+  if (role == 0) {
+    float* dst = xch + side * (S * kUpad);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      dst[j * kWarp + lane] = v0[j];
+      if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
+    }
+    if (lane == 0) xoff[side] = c;
+  }
+  __syncthreads();     // also makes phase A's global scratch visible to the whole CTA
+  if (tid == 0) reset_sync_state();
+  LseAcc zacc;
+  for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(xch[q] + xch[S * kUpad + q]);
+  const float lz = zacc.warp_result();
+  const bool dead = (lz == kNegInf);                          // no feasible alignment: loss = +inf, zero gradient
+  const double lossd_mid = -((double)lz + xoff[0] + xoff[1]);  // -log Z
+  __syncthreads();
+
+  // ------------------------------------------------ phase B ------------------------------------------------------------
+  if (!dead) {
+    if (side == 0) {
+      if (role == 0) rec_phase<NS, CLASSIC, 0, true>(a, f, sv, b, n_t - M, M, +1, v0, v1, c, lb, lane);
+      else worker_phase<NS, CLASSIC, 0, true>(a, f, sv, b, role - 1, n_t - M, M, +1, L, lossd_mid, dl, toks, map, lane);
+    } else {
+      if (role == 0) rec_phase<NS, CLASSIC, 1, true>(a, f, sv, b, M, M - 1, -1, v0, v1, c, lb, lane);
+      else worker_phase<NS, CLASSIC, 1, true>(a, f, sv, b, role - 1, M, M - 1, -1, L, lossd_mid, dl, toks, map, lane);
+    }
+  }
+
+  // ------------------------------------------------ loss and the rows nobody owns --------------------------------------
+  if (side == 0 && role == 0) {
+    // loss = -alpha[T, label_length] (classic_ctc_loss.py:152-165 / simplified_ctc_loss.py:73-83); frames beyond n_t
+    // leave it unchanged.
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+      if (lane * NS + j == L) {
+        const double ld = dead ? (double)INFINITY : -((double)(CLASSIC ? lse2(v0[j], v1[j]) : v0[j]) + c);
+        a.loss[b] = (float)ld;
+      }
+  }
+  if (role > 0) {     // frames beyond logit_length, or every frame of an infeasible sample: exact zeros
+    const int widx = side * W + (role - 1);
+    for (int r = (dead ? 0 : n_t) + widx; r < p.T; r += 2 * W) fused_zero_row(a.grad + ((size_t)b * p.T + r) * p.V, p.V, lane);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------------
+constexpr int kSmemPerSm = 227 * 1024;
+
+// workers per side for this problem, 0 when the fused kernel cannot take it
+int fused_pick_workers(const Problem& p) {
+  if ((p.V & 3) != 0 || p.NS > kMaxNS) return 0;
+  for (int W = kMaxWorkers; W >= 1; --W)
+    if (fused_layout(p.V, p.Upad, p.S, W).total <= kSmemPerSm) return W;   // 2 CTAs/SM when it is <= ~113 KB
+  return 0;
+}
+
+template <int NS, bool CLASSIC>
+static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
+  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W);
+  cudaError_t e = cudaFuncSetAttribute(kf_fused<NS, CLASSIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, f.total);
+  if (e != cudaSuccess) return e;
+  kf_fused<NS, CLASSIC><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss, float* loss, float* grad, int W,
+                         cudaStream_t st) {
+  if (p.B == 0) return cudaSuccess;
+  FusedArgs a;
+  a.p = p;
+  a.rowlse = s.rowlse;
+  a.stateT = s.alphaT;      // the staged path's alpha scratch is large enough ([B,(T+1),S,Upad])
+  a.coff = s.ca;
+  a.d_loss = d_loss;
+  a.loss = loss;
+  a.grad = grad;
+  a.W = W;
+  const bool classic = p.variant == CTCB200_CLASSIC;
+  switch (p.NS) {
+#define CTCB200_CASE(n) \
+  case n:               \
+    return classic ? launch_fused_ns<n, true>(a, st) : launch_fused_ns<n, false>(a, st);
+    CTCB200_CASE(1) CTCB200_CASE(2) CTCB200_CASE(3) CTCB200_CASE(4) CTCB200_CASE(5) CTCB200_CASE(6)
+    CTCB200_CASE(7) CTCB200_CASE(8) CTCB200_CASE(9) CTCB200_CASE(10) CTCB200_CASE(11) CTCB200_CASE(12)
+    CTCB200_CASE(13) CTCB200_CASE(14) CTCB200_CASE(15) CTCB200_CASE(16)
+#undef CTCB200_CASE
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace ctcb200
