@@ -31,7 +31,7 @@
 
 namespace ctcb200 {
 
-constexpr int kRowSlots = 2;        // TMA row buffers per worker (current + prefetch)
+constexpr int kMaxRowSlots = 3;     // TMA row buffers per worker: current + prefetch (+ one draining its TMA store)
 constexpr int kFusedGroup = 4;      // frames per unrolled group (renormalisation cadence, see recursion.cuh)
 constexpr int kMaxWorkers = 3;
 
@@ -73,9 +73,19 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void spin_until(const unsigned* p, unsigned need) {
-  while (ld_acquire(p) < need) {
-  }
+  if (ld_acquire(p) >= need) return;
+  do {
+    __nanosleep(20);      // back off: a waiting warp must not eat the issue slots of the warps it is waiting for
+  } while (ld_acquire(p) < need);
 }
+// 1-D TMA store: shared -> global bulk copy tracked by the per-thread bulk async-group
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fused_cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -84,36 +94,34 @@ __device__ __forceinline__ void fused_cp_async_wait_all() { asm volatile("cp.asy
 
 // ---- shared-memory layout (one definition for host sizing and device carving) ---------------------------------------
 struct FusedLayout {
-  int W, R;                 // workers per side, ring depth (= 2W, a multiple of W)
-  int off_map, off_toks, off_xch, off_xoff, off_side0, total;
+  int W, R, SL;             // workers per side, ring depth (= 2W, a multiple of W), row buffers per worker
+  int off_xch, off_xoff, off_side0, total;
   // offsets inside a side block
-  int s_ctl, s_bar, s_row, s_ringd, s_ringh, s_rings, s_ringc, s_stbuf, s_acc, side_bytes;
+  int s_ctl, s_bar, s_row, s_ringd, s_ringh, s_rings, s_ringc, s_stbuf, side_bytes;
 };
 
 __host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W) {
+__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL) {
   FusedLayout f;
   f.W = W;
   f.R = 2 * W;
+  f.SL = SL;
   int o = 0;
-  f.off_map = o;  o += fl_align(((V + 7) & ~7) * 2, 16);
-  f.off_toks = o; o += Upad * 4;
   f.off_xch = o;  o += 2 * S * Upad * 4;
   f.off_xoff = o; o += 2 * 8;
   o = fl_align(o, 128);
   int s = 0;
   f.s_ctl = s;   s += fl_align((2 * W + 2) * 4, 16);          // dcount[W], done[W], ccount, scount
-  f.s_bar = s;   s += W * kRowSlots * 8;
+  f.s_bar = s;   s += W * kMaxRowSlots * 8;
   s = fl_align(s, 128);
-  f.s_row = s;   s += W * kRowSlots * V * 4;
+  f.s_row = s;   s += W * SL * V * 4;
   f.s_ringd = s; s += f.R * Upad * 4;
   f.s_ringh = s; s += fl_align(f.R * 4, 16);
   f.s_rings = s; s += f.R * S * Upad * 4;
   f.s_ringc = s; s += f.R * 8;
   s = fl_align(s, 16);
   f.s_stbuf = s; s += W * S * Upad * 4;
-  f.s_acc = s;   s += W * (Upad + kWarp) * 4;
   f.side_bytes = fl_align(s, 128);
   f.off_side0 = o;
   f.total = o + 2 * f.side_bytes;
@@ -128,7 +136,7 @@ struct FusedArgs {
   const float* d_loss;  // [B] or null
   float* loss;          // [B]
   float* grad;          // [B,T,V]
-  int W;
+  int W, SL;
 };
 
 // view of one side's shared memory
@@ -137,14 +145,13 @@ struct SideView {
   unsigned* done;     // [W] rows each worker has completely finished (phase B)
   unsigned* ccount;   // frames the recursion warp has consumed
   unsigned* scount;   // frames whose pre-step state the recursion warp has published (phase B)
-  unsigned long long* bar;   // [W][kRowSlots]
-  float* row;         // [W][kRowSlots][V]
+  unsigned long long* bar;   // [W][kMaxRowSlots]
+  float* row;         // [W][SL][V]
   float* ringd;       // [R][Upad]
   float* ringh;       // [R]
   float* rings;       // [R][S*Upad]
   double* ringc;      // [R]
   float* stbuf;       // [W][S*Upad]
-  float* acc;         // [W][Upad+32]
 };
 
 __device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLayout& f, int side) {
@@ -162,7 +169,6 @@ __device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLa
   v.rings = reinterpret_cast<float*>(base + f.s_rings);
   v.ringc = reinterpret_cast<double*>(base + f.s_ringc);
   v.stbuf = reinterpret_cast<float*>(base + f.s_stbuf);
-  v.acc = reinterpret_cast<float*>(base + f.s_acc);
   return v;
 }
 
@@ -242,37 +248,35 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
 }
 
 // ---- row worker, one phase -------------------------------------------------------------------------------------------
+// tok[j] = cleaned label (base_loss.py:395-418) of this lane's states l = lane*NS + j, tok_left = label of state
+// lane*NS - 1; they live in registers for the whole kernel.
 template <int NS, bool CLASSIC, int SIDE, bool PHASE_B>
 __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int b, int w,
                                              int count, int t_first, int t_step, int L, double lossd_mid, float dl,
-                                             const int* toks, const unsigned short* map, int lane) {
+                                             const int (&tok)[NS], int tok_left, int lane) {
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
+  constexpr float kLog2e = 1.4426950408889634f;
   const Problem& p = a.p;
-  const int W = f.W, R = f.R, V = p.V, n4 = V >> 2;
+  const int W = f.W, R = f.R, SL = f.SL, V = p.V, n4 = V >> 2;
   const int n_my = (count > w) ? (count - w + W - 1) / W : 0;
   const unsigned row_bytes = (unsigned)V * 4u;
   const float* logits_b = p.logits + (size_t)b * p.T * V;
-  float* rowbuf = sv.row + (size_t)w * kRowSlots * V;
-  unsigned long long* bars = sv.bar + w * kRowSlots;
+  float* rowbuf = sv.row + (size_t)w * SL * V;
+  unsigned long long* bars = sv.bar + w * kMaxRowSlots;
   float* stb = sv.stbuf + w * (S * kUpad);
-  float* acc = sv.acc + w * (kUpad + kWarp);
 
-  if (n_my > 0 && lane == 0) {
-    const int t = t_first + w * t_step;
-    mbar_expect_tx(bars + 0, row_bytes);
-    bulk_load(rowbuf, logits_b + (size_t)t * V, row_bytes, bars + 0);
-  }
-  int slot = w % R;    // ring slot of frame i = w + n*W
+  // prologue: the first SL-1 rows are in flight before any is consumed
+  if (lane == 0)
+    for (int q = 0; q < SL - 1 && q < n_my; ++q) {
+      mbar_expect_tx(bars + q, row_bytes);
+      bulk_load(rowbuf + (size_t)q * V, logits_b + (size_t)(t_first + (w + q * W) * t_step) * V, row_bytes, bars + q);
+    }
+  int slot = w % R;        // ring slot of frame i = w + n*W
+  int rs = 0;              // row buffer of row n (= n % SL)
+  unsigned par = 0;        // bit q: parity of the next completion to wait for on row buffer q
   for (int n = 0; n < n_my; ++n) {
     const int i = w + n * W;
     const int t = t_first + i * t_step;
-    const int rs = n & 1;
-    // prefetch the next row into the other buffer (its previous occupant was finished in the last iteration)
-    if (n + 1 < n_my && lane == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(bars + (rs ^ 1), row_bytes);
-      bulk_load(rowbuf + (size_t)(rs ^ 1) * V, logits_b + (size_t)(t + W * t_step) * V, row_bytes, bars + (rs ^ 1));
-    }
     float lse = 0.0f;
     double cst = 0.0;
     if (PHASE_B) {
@@ -284,80 +288,178 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
         if (cidx < S * kUpad / 4) fused_cp_async16(stb + 4 * cidx, src + 4 * cidx);
       }
       fused_cp_async_commit();
-      if (!p.input_logprobas) lse = a.rowlse[(size_t)b * p.T + t];   // written in phase A by this CTA: plain (coherent) load
+      if (!p.input_logprobas) lse = a.rowlse[(size_t)b * p.T + t];   // written in phase A by this CTA: plain load
       cst = a.coff[(size_t)b * p.T + t];
     }
-    mbar_wait(bars + rs, (unsigned)((n >> 1) & 1));            // the row has landed
-    const float* row = rowbuf + (size_t)rs * V;
-    const float4* row4 = reinterpret_cast<const float4*>(row);
+    mbar_wait(bars + rs, (par >> rs) & 1u);                    // the row has landed
+    par ^= 1u << rs;
+    float* row = rowbuf + (size_t)rs * V;
+    float4* row4 = reinterpret_cast<float4*>(row);
 
-    // ---- stage 1: row statistics (phase A) and the gather of the label columns ----
+    // ---- stage 1: row log-sum-exp (phase A; one pass, the row chunk lives in registers) and the label gather ----
     if (!PHASE_B && !p.input_logprobas) {
-      float m = kNegInf;
-      for (int c4 = lane; c4 < n4; c4 += kWarp) {
-        const float4 v = row4[c4];
-        m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+      float m_run = kNegInf, s_run = 0.0f;
+      for (int base = 0; base < n4; base += 8 * kWarp) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c4 = base + u * kWarp + lane;
+          v[u] = (c4 < n4) ? row4[c4] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+        }
+        float cm = kNegInf;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cm = fmaxf(fmaxf(cm, fmaxf(v[u].x, v[u].y)), fmaxf(v[u].z, v[u].w));
+        const float mn = fmaxf(m_run, cm);
+        const float mn0 = (mn == kNegInf || mn == INFINITY) ? 0.0f : mn;     // tf.reduce_logsumexp convention
+        s_run *= ex2_approx((m_run - mn0) * kLog2e);                         // 0 * 0 when m_run == -inf
+        // (v - max) first, then the scale: a fused v*log2e - max*log2e would lose the exact 0 for |logit| ~ 1e10
+        float cs = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          cs += (ex2_approx((v[u].x - mn0) * kLog2e) + ex2_approx((v[u].y - mn0) * kLog2e)) +
+                (ex2_approx((v[u].z - mn0) * kLog2e) + ex2_approx((v[u].w - mn0) * kLog2e));
+        s_run += cs;
+        m_run = mn;
       }
-      m = warp_max(m);
-      const float m0 = (m == kNegInf || m == INFINITY) ? 0.0f : m;   // tf.reduce_logsumexp convention
-      float sum = 0.0f;
-      for (int c4 = lane; c4 < n4; c4 += kWarp) {
-        const float4 v = row4[c4];
-        sum += (__expf(v.x - m0) + __expf(v.y - m0)) + (__expf(v.z - m0) + __expf(v.w - m0));
-      }
-      sum = warp_sum(sum);
-      lse = m0 + logf(sum);
+      const float M = warp_max(m_run);
+      const float M0 = (M == kNegInf || M == INFINITY) ? 0.0f : M;
+      const float mr0 = (m_run == kNegInf || m_run == INFINITY) ? 0.0f : m_run;
+      const float sum = warp_sum(s_run * ex2_approx((mr0 - M0) * kLog2e));
+      lse = M0 + logf(sum);
       if (lane == 0) a.rowlse[(size_t)b * p.T + t] = lse;
     }
     if (!PHASE_B && i >= R) spin_until(sv.ccount, (unsigned)(i - R + 1));   // ring slot consumed by the recursion
+    float dd[NS];
     {
-      float* dd = sv.ringd + slot * kUpad;
+      float* dst = sv.ringd + slot * kUpad;
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         const int l = lane * NS + j;
-        float v = kNegInf;
-        if (l < L) {
-          const int tok = toks[l];
-          if (tok >= 0 && tok < V) v = row[tok] - lse;
-        }
-        dd[j * kWarp + lane] = v;
+        const bool ok = (l < L) && (tok[j] >= 0) && (tok[j] < V);
+        dd[j] = ok ? row[ok ? tok[j] : 0] - lse : kNegInf;
+        dst[j * kWarp + lane] = dd[j];
       }
-      if (lane == 0) sv.ringh[slot] = row[p.blank] - lse;
     }
+    const float h = row[p.blank] - lse;
+    if (lane == 0) sv.ringh[slot] = h;
     __syncwarp();
     if (lane == 0) st_release(sv.dcount + w, (unsigned)(n + 1));
 
-    // ---- stage 2 (phase B): occupancies of the frame and the dense gradient row ----
+    // ---- prefetch: row n+SL-1 goes into the buffer row n-1 used; its TMA store (phase B) must have drained ----
+    if (lane == 0 && n + SL - 1 < n_my) {
+      const int q = (rs == 0) ? SL - 1 : rs - 1;
+      if (PHASE_B) bulk_store_wait_read();
+      fence_proxy_async();
+      mbar_expect_tx(bars + q, row_bytes);
+      bulk_load(rowbuf + (size_t)q * V, logits_b + (size_t)(t + (SL - 1) * W * t_step) * V, row_bytes, bars + q);
+    }
+
+    // ---- stage 2 (phase B): occupancies of the frame, then the dense gradient row ----
     if (PHASE_B) {
       spin_until(sv.scount, (unsigned)(i + 1));                 // the running side's state for this frame is published
       fused_cp_async_wait_all();
       __syncwarp();
       const float* ring_state = sv.rings + slot * (S * kUpad);
-      const float lossb = (float)(lossd_mid + sv.ringc[slot] + cst);
+      const float K = (float)(lossd_mid + sv.ringc[slot] + cst);   // loss + both renormalisation offsets
       const float* A = (SIDE == 0) ? ring_state : stb;         // alpha[t]
       const float* Bn = (SIDE == 0) ? stb : ring_state;        // beta[t+1]
-      const float occ_sum =
-          row_occupancies<CLASSIC>(p, L, lane, A, Bn, sv.ringd + slot * kUpad, sv.ringh[slot], lossb, toks, map, acc);
+      float occ[NS], occ_stay[NS], x[NS];
+      float xm = kNegInf, osum = 0.0f;
+      if (!CLASSIC) {
+        float a0[NS], b0[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          a0[j] = A[j * kWarp + lane];
+          b0[j] = Bn[j * kWarp + lane];
+        }
+        float bx = __shfl_down_sync(kFull, b0[0], 1);
+        if (lane == 31) bx = kNegInf;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          x[j] = a0[j] + b0[j];                                 // blank keeps the state: simplified_ctc_loss.py:498-501
+          xm = fmaxf(xm, x[j]);
+          const float bn = (j < NS - 1) ? b0[j + 1] : bx;
+          occ[j] = ex2_approx((K + (a0[j] + dd[j] + bn)) * kLog2e);   // emit label[l]: simplified_ctc_loss.py:503-510
+          const bool ok = (tok[j] != p.blank) && (tok[j] >= 0) && (tok[j] < V);
+          if (!ok) occ[j] = 0.0f;
+          osum += occ[j];
+        }
+      } else {
+        float a0[NS], a1[NS], b0[NS], b1[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          a0[j] = A[j * kWarp + lane];
+          a1[j] = A[kUpad + j * kWarp + lane];
+          b0[j] = Bn[j * kWarp + lane];
+          b1[j] = Bn[kUpad + j * kWarp + lane];
+        }
+        float bx = __shfl_down_sync(kFull, b1[0], 1);
+        if (lane == 31) bx = kNegInf;
+        float d_left = __shfl_up_sync(kFull, dd[NS - 1], 1);
+        if (lane == 0) d_left = kNegInf;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          const int tp = (j > 0) ? tok[j - 1] : tok_left;
+          const float sj = lse2(a0[j], a1[j]);
+          x[j] = sj + b0[j];                                    // any state -> closed via blank: classic_ctc_loss.py:608-614
+          xm = fmaxf(xm, x[j]);
+          const float bn = (j < NS - 1) ? b1[j + 1] : bx;
+          // diagonal step emitting label[l] (classic_ctc_loss.py:629-639); open -> open is barred on a repeat
+          occ[j] = ex2_approx((K + (dd[j] + ((tok[j] == tp) ? a0[j] : sj) + bn)) * kLog2e);
+          if (!((tok[j] != p.blank) && (tok[j] >= 0) && (tok[j] < V))) occ[j] = 0.0f;
+          // horizontal step re-emitting label[l-1] from the open state (classic_ctc_loss.py:617-626)
+          const float dp = (j > 0) ? dd[j - 1] : d_left;
+          occ_stay[j] = ex2_approx((K + (a1[j] + dp + b1[j])) * kLog2e);
+          if (!((tp != p.blank) && (tp >= 0) && (tp < V))) occ_stay[j] = 0.0f;
+          osum += occ[j] + occ_stay[j];
+        }
+      }
+      const float XM = warp_max(xm);
+      const float XM0 = (XM == kNegInf) ? 0.0f : XM;
+      float xs = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) xs += ex2_approx((x[j] - XM0) * kLog2e);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        xs += __shfl_xor_sync(kFull, xs, o);
+        osum += __shfl_xor_sync(kFull, osum, o);
+      }
+      const float occ_blank = (XM == kNegInf) ? 0.0f : __expf(K + (h + (XM + __logf(xs))));
+      const float occ_sum = osum + occ_blank;
+
+      // dense row in place: softmax * d_loss * sum(occ); then the <= U+1 occupancies are subtracted by scatter
       const float scale = dl * occ_sum;
-      float4* out4 = reinterpret_cast<float4*>(a.grad + ((size_t)b * p.T + t) * V);
-      const ushort4* m4 = reinterpret_cast<const ushort4*>(map);
-#pragma unroll 4
+#pragma unroll 8
       for (int c4 = lane; c4 < n4; c4 += kWarp) {
-        const float4 v = row4[c4];
-        const ushort4 m = m4[c4];
-        float4 g;
-        g.x = scale * __expf(v.x - lse) - ((m.x != kNoSlot) ? dl * acc[m.x] : 0.0f);
-        g.y = scale * __expf(v.y - lse) - ((m.y != kNoSlot) ? dl * acc[m.y] : 0.0f);
-        g.z = scale * __expf(v.z - lse) - ((m.z != kNoSlot) ? dl * acc[m.z] : 0.0f);
-        g.w = scale * __expf(v.w - lse) - ((m.w != kNoSlot) ? dl * acc[m.w] : 0.0f);
-        stg_stream4(out4 + c4, g);
+        float4 v = row4[c4];
+        v.x = scale * ex2_approx((v.x - lse) * kLog2e);
+        v.y = scale * ex2_approx((v.y - lse) * kLog2e);
+        v.z = scale * ex2_approx((v.z - lse) * kLog2e);
+        v.w = scale * ex2_approx((v.w - lse) * kLog2e);
+        row4[c4] = v;
       }
       __syncwarp();
-      if (lane == 0) st_release(sv.done + w, (unsigned)(n + 1));
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        if (occ[j] > 0.0f) atomicAdd(&row[tok[j]], -dl * occ[j]);
+        if (CLASSIC) {
+          const int tp = (j > 0) ? tok[j - 1] : tok_left;
+          if (occ_stay[j] > 0.0f) atomicAdd(&row[tp], -dl * occ_stay[j]);
+        }
+      }
+      if (lane == 0) atomicAdd(&row[p.blank], -dl * occ_blank);
+      __syncwarp();
+      if (lane == 0) {
+        fence_proxy_async();                                    // generic-proxy writes -> visible to the TMA store
+        bulk_store(a.grad + ((size_t)b * p.T + t) * V, row, row_bytes);
+        st_release(sv.done + w, (unsigned)(n + 1));             // state-ring slot and stb are free again
+      }
     }
     slot += W;
     if (slot >= R) slot -= R;
+    if (++rs == SL) rs = 0;
   }
+  if (PHASE_B && lane == 0) bulk_store_wait_read();             // shared memory must outlive the stores reading it
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
@@ -366,15 +468,13 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const Problem& p = a.p;
-  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W);
+  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = f.W;
   const int side = warp / (W + 1), role = warp % (W + 1);      // role 0 = recursion warp, 1..W = row workers
   const int L = utt_label_len(p, b), n_t = utt_frames(p, b), M = n_t >> 1;
   const float dl = a.d_loss ? a.d_loss[b] : 1.0f;
 
-  unsigned short* map = reinterpret_cast<unsigned short*>(smem + f.off_map);
-  int* toks = reinterpret_cast<int*>(smem + f.off_toks);
   float* xch = reinterpret_cast<float*>(smem + f.off_xch);
   double* xoff = reinterpret_cast<double*>(smem + f.off_xoff);
   const SideView sv = side_view(smem, f, side);
@@ -383,14 +483,19 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
     for (int s2 = 0; s2 < 2; ++s2) {
       const SideView v = side_view(smem, f, s2);
       for (int k = 0; k < 2 * W + 2; ++k) v.dcount[k] = 0u;
-      for (int k = 0; k < W * kRowSlots; ++k) mbar_init(v.bar + k, 1u);
+      for (int k = 0; k < W * kMaxRowSlots; ++k) mbar_init(v.bar + k, 1u);
     }
     fence_mbar_init();
   };
 
-  build_utterance_tables(p, b, L, toks, map, (p.V + 7) & ~7);   // ends with __syncthreads
   if (tid == 0) reset_sync_state();
   __syncthreads();
+
+  // this lane's labels, in registers for the whole kernel
+  int tok[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) tok[j] = utt_token(p, b, lane * NS + j, L);
+  const int tok_left = utt_token(p, b, lane * NS - 1, L);
 
   // recursion state (only meaningful in the two recursion warps)
   float v0[NS], v1[NS];
@@ -412,10 +517,10 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
   // ------------------------------------------------ phase A ------------------------------------------------------------
   if (side == 0) {
     if (role == 0) rec_phase<NS, CLASSIC, 0, false>(a, f, sv, b, M, 0, +1, v0, v1, c, lb, lane);
-    else worker_phase<NS, CLASSIC, 0, false>(a, f, sv, b, role - 1, M, 0, +1, L, 0.0, dl, toks, map, lane);
+    else worker_phase<NS, CLASSIC, 0, false>(a, f, sv, b, role - 1, M, 0, +1, L, 0.0, dl, tok, tok_left, lane);
   } else {
     if (role == 0) rec_phase<NS, CLASSIC, 1, false>(a, f, sv, b, n_t - M, n_t - 1, -1, v0, v1, c, lb, lane);
-    else worker_phase<NS, CLASSIC, 1, false>(a, f, sv, b, role - 1, n_t - M, n_t - 1, -1, L, 0.0, dl, toks, map, lane);
+    else worker_phase<NS, CLASSIC, 1, false>(a, f, sv, b, role - 1, n_t - M, n_t - 1, -1, L, 0.0, dl, tok, tok_left, lane);
   }
 
   // ------------------------------------------------ the middle ---------------------------------------------------------
@@ -441,10 +546,10 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
   if (!dead) {
     if (side == 0) {
       if (role == 0) rec_phase<NS, CLASSIC, 0, true>(a, f, sv, b, n_t - M, M, +1, v0, v1, c, lb, lane);
-      else worker_phase<NS, CLASSIC, 0, true>(a, f, sv, b, role - 1, n_t - M, M, +1, L, lossd_mid, dl, toks, map, lane);
+      else worker_phase<NS, CLASSIC, 0, true>(a, f, sv, b, role - 1, n_t - M, M, +1, L, lossd_mid, dl, tok, tok_left, lane);
     } else {
       if (role == 0) rec_phase<NS, CLASSIC, 1, true>(a, f, sv, b, M, M - 1, -1, v0, v1, c, lb, lane);
-      else worker_phase<NS, CLASSIC, 1, true>(a, f, sv, b, role - 1, M, M - 1, -1, L, lossd_mid, dl, toks, map, lane);
+      else worker_phase<NS, CLASSIC, 1, true>(a, f, sv, b, role - 1, M, M - 1, -1, L, lossd_mid, dl, tok, tok_left, lane);
     }
   }
 
@@ -468,17 +573,31 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
 // ---- host side -------------------------------------------------------------------------------------------------------------
 constexpr int kSmemPerSm = 227 * 1024;
 
-// workers per side for this problem, 0 when the fused kernel cannot take it
+// (workers per side, row buffers per worker) for this problem; W == 0 when the fused kernel cannot take it.
+// Preference: configurations that leave room for two CTAs per SM (more warps to hide latency), then one CTA per SM.
+static bool fused_pick(const Problem& p, int* W, int* SL) {
+  *W = 0; *SL = 0;
+  if ((p.V & 3) != 0 || p.NS > kMaxNS) return false;
+  static const int cand[5][2] = {{3, 3}, {3, 2}, {2, 3}, {2, 2}, {1, 2}};
+  const int budgets[2] = {kSmemPerSm / 2 - 1024, kSmemPerSm};
+  for (int bi = 0; bi < 2; ++bi)
+    for (int c = 0; c < 5; ++c)
+      if (fused_layout(p.V, p.Upad, p.S, cand[c][0], cand[c][1]).total <= budgets[bi]) {
+        *W = cand[c][0]; *SL = cand[c][1];
+        return true;
+      }
+  return false;
+}
+
 int fused_pick_workers(const Problem& p) {
-  if ((p.V & 3) != 0 || p.NS > kMaxNS) return 0;
-  for (int W = kMaxWorkers; W >= 1; --W)
-    if (fused_layout(p.V, p.Upad, p.S, W).total <= kSmemPerSm) return W;   // 2 CTAs/SM when it is <= ~113 KB
-  return 0;
+  int W, SL;
+  fused_pick(p, &W, &SL);
+  return W;
 }
 
 template <int NS, bool CLASSIC>
 static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
-  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W);
+  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL);
   cudaError_t e = cudaFuncSetAttribute(kf_fused<NS, CLASSIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, f.total);
   if (e != cudaSuccess) return e;
   kf_fused<NS, CLASSIC><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
@@ -496,7 +615,8 @@ cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss
   a.d_loss = d_loss;
   a.loss = loss;
   a.grad = grad;
-  a.W = W;
+  fused_pick(p, &a.W, &a.SL);
+  (void)W;
   const bool classic = p.variant == CTCB200_CLASSIC;
   switch (p.NS) {
 #define CTCB200_CASE(n) \
