@@ -20,7 +20,7 @@ MAX_STATES = 512
 MAX_TOKENS = 32768
 
 _LIB_NAME = "libctc_b200.so"
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+_LIB_PATH = os.environ.get("CTCB200_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME))
 
 EXPORTED_SYMBOLS = (
     "ctcb200_version", "ctcb200_strerror", "ctcb200_stage_names", "ctcb200_launches_per_call",

@@ -25,6 +25,8 @@
 //                    occupancies (occupancy.cuh) and streams out the dense gradient row with 128-bit stores.
 // Warps hand work to each other through monotonic counters in shared memory (st.release / ld.acquire at CTA scope);
 // there is no CTA-wide barrier inside a phase.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "occupancy.cuh"
 #include "recursion.cuh"
@@ -33,7 +35,7 @@ namespace ctcb200 {
 
 constexpr int kMaxRowSlots = 3;     // TMA row buffers per worker: current + prefetch (+ one draining its TMA store)
 constexpr int kFusedGroup = 4;      // frames per unrolled group (renormalisation cadence, see recursion.cuh)
-constexpr int kMaxWorkers = 3;
+constexpr int kMaxWorkers = 4;
 
 // ---- PTX helpers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -92,6 +94,23 @@ __device__ __forceinline__ void fused_cp_async16(void* smem_dst, const void* gsr
 __device__ __forceinline__ void fused_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void fused_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// ---- optional wait-time instrumentation (compile with -DCTCB200_FUSED_TIMING; results go to FusedArgs::dbg) --------
+// per warp: [0] phase A cycles, [1] phase B cycles, [2] TMA wait, [3] dcount wait, [4] ccount wait, [5] scount wait,
+//           [6] done wait, [7] state cp.async wait
+#ifdef CTCB200_FUSED_TIMING
+#define TIMED(slot, stmt)                       \
+  do {                                          \
+    const long long t0__ = clock64();           \
+    stmt;                                       \
+    tm[slot] += clock64() - t0__;               \
+  } while (0)
+#else
+#define TIMED(slot, stmt) \
+  do {                    \
+    stmt;                 \
+  } while (0)
+#endif
+
 // ---- shared-memory layout (one definition for host sizing and device carving) ---------------------------------------
 struct FusedLayout {
   int W, R, SL;             // workers per side, ring depth (= 2W, a multiple of W), row buffers per worker
@@ -137,6 +156,7 @@ struct FusedArgs {
   float* loss;          // [B]
   float* grad;          // [B,T,V]
   int W, SL;
+  long long* dbg;       // [B][warps][8] when built with CTCB200_FUSED_TIMING, else unused
 };
 
 // view of one side's shared memory
@@ -183,7 +203,7 @@ __device__ __forceinline__ void fused_zero_row(float* dst, int V, int lane) {
 template <int NS, bool CLASSIC, int SIDE, bool PHASE_B>
 __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int b, int count,
                                           int t_first, int t_step, float* v0, float* v1, double& c,
-                                          const LabelBits<NS>& lb, int lane) {
+                                          const LabelBits<NS>& lb, int lane, long long* tm) {
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const int W = f.W, R = f.R;
   float m_pend = kNegInf;
@@ -198,7 +218,7 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
     for (int k = 0; k < kFusedGroup; ++k) {
       const int i = i0 + k;
       if (i < count) {
-        spin_until(sv.dcount + w, (unsigned)(n + 1));          // the frame's inputs are in the ring
+        TIMED(3, spin_until(sv.dcount + w, (unsigned)(n + 1)));   // the frame's inputs are in the ring
         float d[NS];
         const float* dsrc = sv.ringd + slot * kUpad;
 #pragma unroll
@@ -218,7 +238,7 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
           g_off += t_step;
         } else {
           if (i >= R) {                                          // the state slot's previous frame is fully processed
-            spin_until(sv.done + wj, (unsigned)(nj + 1));
+            TIMED(6, spin_until(sv.done + wj, (unsigned)(nj + 1)));
             if (++wj == W) { wj = 0; ++nj; }
           }
           float* dst = sv.rings + slot * (S * kUpad);
@@ -249,11 +269,12 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
 
 // ---- row worker, one phase -------------------------------------------------------------------------------------------
 // tok[j] = cleaned label (base_loss.py:395-418) of this lane's states l = lane*NS + j, tok_left = label of state
-// lane*NS - 1; they live in registers for the whole kernel.
-template <int NS, bool CLASSIC, int SIDE, bool PHASE_B>
-__device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int b, int w,
-                                             int count, int t_first, int t_step, int L, double lossd_mid, float dl,
-                                             const int (&tok)[NS], int tok_left, int lane) {
+// lane*NS - 1; they live in registers for the whole kernel.  `side` is a runtime argument (one code body for both
+// sides keeps the instruction footprint inside the instruction cache).
+template <int NS, bool CLASSIC, bool PHASE_B>
+__device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int side, int b,
+                                          int w, int count, int t_first, int t_step, int L, double lossd_mid, float dl,
+                                          const int (&tok)[NS], int tok_left, int lane, long long* tm) {
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   constexpr float kLog2e = 1.4426950408889634f;
   const Problem& p = a.p;
@@ -264,6 +285,8 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   float* rowbuf = sv.row + (size_t)w * SL * V;
   unsigned long long* bars = sv.bar + w * kMaxRowSlots;
   float* stb = sv.stbuf + w * (S * kUpad);
+  const float* rowlse_b = a.rowlse + (size_t)b * p.T;
+  const double* coff_b = a.coff + (size_t)b * p.T;
 
   // prologue: the first SL-1 rows are in flight before any is consumed
   if (lane == 0)
@@ -274,11 +297,19 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   int slot = w % R;        // ring slot of frame i = w + n*W
   int rs = 0;              // row buffer of row n (= n % SL)
   unsigned par = 0;        // bit q: parity of the next completion to wait for on row buffer q
+  // scalars of the row produced in phase A, fetched one row ahead (plain loads: written by this CTA in phase A)
+  float lse_next = 0.0f;
+  double cst_next = 0.0;
+  if (PHASE_B && n_my > 0) {
+    const int t0 = t_first + w * t_step;
+    if (!p.input_logprobas) lse_next = rowlse_b[t0];
+    cst_next = coff_b[t0];
+  }
   for (int n = 0; n < n_my; ++n) {
     const int i = w + n * W;
     const int t = t_first + i * t_step;
-    float lse = 0.0f;
-    double cst = 0.0;
+    float lse = lse_next;
+    const double cst = cst_next;
     if (PHASE_B) {
       // the other side's stored state for this frame: async copy now, consumed after the recursion catches up
       const float* src = a.stateT + ((size_t)b * p.T + t) * (size_t)(S * kUpad);
@@ -288,10 +319,13 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
         if (cidx < S * kUpad / 4) fused_cp_async16(stb + 4 * cidx, src + 4 * cidx);
       }
       fused_cp_async_commit();
-      if (!p.input_logprobas) lse = a.rowlse[(size_t)b * p.T + t];   // written in phase A by this CTA: plain load
-      cst = a.coff[(size_t)b * p.T + t];
+      if (n + 1 < n_my) {
+        const int tn = t + W * t_step;
+        if (!p.input_logprobas) lse_next = rowlse_b[tn];
+        cst_next = coff_b[tn];
+      }
     }
-    mbar_wait(bars + rs, (par >> rs) & 1u);                    // the row has landed
+    TIMED(2, mbar_wait(bars + rs, (par >> rs) & 1u));          // the row has landed
     par ^= 1u << rs;
     float* row = rowbuf + (size_t)rs * V;
     float4* row4 = reinterpret_cast<float4*>(row);
@@ -306,19 +340,20 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           const int c4 = base + u * kWarp + lane;
           v[u] = (c4 < n4) ? row4[c4] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
         }
-        float cm = kNegInf;
+        float pm[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) cm = fmaxf(fmaxf(cm, fmaxf(v[u].x, v[u].y)), fmaxf(v[u].z, v[u].w));
+        for (int u = 0; u < 8; ++u) pm[u] = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+        const float cm = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
         const float mn = fmaxf(m_run, cm);
         const float mn0 = (mn == kNegInf || mn == INFINITY) ? 0.0f : mn;     // tf.reduce_logsumexp convention
         s_run *= ex2_approx((m_run - mn0) * kLog2e);                         // 0 * 0 when m_run == -inf
         // (v - max) first, then the scale: a fused v*log2e - max*log2e would lose the exact 0 for |logit| ~ 1e10
-        float cs = 0.0f;
+        float ps[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          cs += (ex2_approx((v[u].x - mn0) * kLog2e) + ex2_approx((v[u].y - mn0) * kLog2e)) +
-                (ex2_approx((v[u].z - mn0) * kLog2e) + ex2_approx((v[u].w - mn0) * kLog2e));
-        s_run += cs;
+          ps[u] = (ex2_approx((v[u].x - mn0) * kLog2e) + ex2_approx((v[u].y - mn0) * kLog2e)) +
+                  (ex2_approx((v[u].z - mn0) * kLog2e) + ex2_approx((v[u].w - mn0) * kLog2e));
+        s_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
         m_run = mn;
       }
       const float M = warp_max(m_run);
@@ -328,7 +363,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       lse = M0 + logf(sum);
       if (lane == 0) a.rowlse[(size_t)b * p.T + t] = lse;
     }
-    if (!PHASE_B && i >= R) spin_until(sv.ccount, (unsigned)(i - R + 1));   // ring slot consumed by the recursion
+    if (!PHASE_B && i >= R) TIMED(4, spin_until(sv.ccount, (unsigned)(i - R + 1)));   // ring slot consumed by the recursion
     float dd[NS];
     {
       float* dst = sv.ringd + slot * kUpad;
@@ -345,6 +380,21 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     __syncwarp();
     if (lane == 0) st_release(sv.dcount + w, (unsigned)(n + 1));
 
+    // ---- stage 1b (phase B): the dense softmax part of the gradient row, in place, while the recursion catches up.
+    // d loss/d logit = d_loss * (softmax * sum_k occ - occ); sum_k occ is 1 for every frame of a feasible sample (it is
+    // the total probability of being somewhere), so the softmax term does not have to wait for the occupancies.
+    if (PHASE_B) {
+#pragma unroll 8
+      for (int c4 = lane; c4 < n4; c4 += kWarp) {
+        float4 v = row4[c4];
+        v.x = dl * ex2_approx((v.x - lse) * kLog2e);
+        v.y = dl * ex2_approx((v.y - lse) * kLog2e);
+        v.z = dl * ex2_approx((v.z - lse) * kLog2e);
+        v.w = dl * ex2_approx((v.w - lse) * kLog2e);
+        row4[c4] = v;
+      }
+    }
+
     // ---- prefetch: row n+SL-1 goes into the buffer row n-1 used; its TMA store (phase B) must have drained ----
     if (lane == 0 && n + SL - 1 < n_my) {
       const int q = (rs == 0) ? SL - 1 : rs - 1;
@@ -354,17 +404,17 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       bulk_load(rowbuf + (size_t)q * V, logits_b + (size_t)(t + (SL - 1) * W * t_step) * V, row_bytes, bars + q);
     }
 
-    // ---- stage 2 (phase B): occupancies of the frame, then the dense gradient row ----
+    // ---- stage 2 (phase B): occupancies of the frame, scattered into the row; then the row leaves by TMA ----
     if (PHASE_B) {
-      spin_until(sv.scount, (unsigned)(i + 1));                 // the running side's state for this frame is published
-      fused_cp_async_wait_all();
+      TIMED(5, spin_until(sv.scount, (unsigned)(i + 1)));      // the running side's state for this frame is published
+      TIMED(7, fused_cp_async_wait_all());
       __syncwarp();
       const float* ring_state = sv.rings + slot * (S * kUpad);
       const float K = (float)(lossd_mid + sv.ringc[slot] + cst);   // loss + both renormalisation offsets
-      const float* A = (SIDE == 0) ? ring_state : stb;         // alpha[t]
-      const float* Bn = (SIDE == 0) ? stb : ring_state;        // beta[t+1]
+      const float* A = (side == 0) ? ring_state : stb;         // alpha[t]
+      const float* Bn = (side == 0) ? stb : ring_state;        // beta[t+1]
       float occ[NS], occ_stay[NS], x[NS];
-      float xm = kNegInf, osum = 0.0f;
+      float xm = kNegInf;
       if (!CLASSIC) {
         float a0[NS], b0[NS];
 #pragma unroll
@@ -382,7 +432,6 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           occ[j] = ex2_approx((K + (a0[j] + dd[j] + bn)) * kLog2e);   // emit label[l]: simplified_ctc_loss.py:503-510
           const bool ok = (tok[j] != p.blank) && (tok[j] >= 0) && (tok[j] < V);
           if (!ok) occ[j] = 0.0f;
-          osum += occ[j];
         }
       } else {
         float a0[NS], a1[NS], b0[NS], b1[NS];
@@ -411,34 +460,9 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           const float dp = (j > 0) ? dd[j - 1] : d_left;
           occ_stay[j] = ex2_approx((K + (a1[j] + dp + b1[j])) * kLog2e);
           if (!((tp != p.blank) && (tp >= 0) && (tp < V))) occ_stay[j] = 0.0f;
-          osum += occ[j] + occ_stay[j];
         }
       }
-      const float XM = warp_max(xm);
-      const float XM0 = (XM == kNegInf) ? 0.0f : XM;
-      float xs = 0.0f;
-#pragma unroll
-      for (int j = 0; j < NS; ++j) xs += ex2_approx((x[j] - XM0) * kLog2e);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        xs += __shfl_xor_sync(kFull, xs, o);
-        osum += __shfl_xor_sync(kFull, osum, o);
-      }
-      const float occ_blank = (XM == kNegInf) ? 0.0f : __expf(K + (h + (XM + __logf(xs))));
-      const float occ_sum = osum + occ_blank;
-
-      // dense row in place: softmax * d_loss * sum(occ); then the <= U+1 occupancies are subtracted by scatter
-      const float scale = dl * occ_sum;
-#pragma unroll 8
-      for (int c4 = lane; c4 < n4; c4 += kWarp) {
-        float4 v = row4[c4];
-        v.x = scale * ex2_approx((v.x - lse) * kLog2e);
-        v.y = scale * ex2_approx((v.y - lse) * kLog2e);
-        v.z = scale * ex2_approx((v.z - lse) * kLog2e);
-        v.w = scale * ex2_approx((v.w - lse) * kLog2e);
-        row4[c4] = v;
-      }
-      __syncwarp();
+      // scatter first (needs no reduction), then the blank column: h + logsumexp_l(x[l])
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         if (occ[j] > 0.0f) atomicAdd(&row[tok[j]], -dl * occ[j]);
@@ -447,6 +471,13 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           if (occ_stay[j] > 0.0f) atomicAdd(&row[tp], -dl * occ_stay[j]);
         }
       }
+      const float XM = warp_max(xm);
+      const float XM0 = (XM == kNegInf) ? 0.0f : XM;
+      float xs = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) xs += ex2_approx((x[j] - XM0) * kLog2e);
+      xs = warp_sum(xs);
+      const float occ_blank = (XM == kNegInf) ? 0.0f : __expf(K + (h + (XM + __logf(xs))));
       if (lane == 0) atomicAdd(&row[p.blank], -dl * occ_blank);
       __syncwarp();
       if (lane == 0) {
@@ -464,7 +495,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
 template <int NS, bool CLASSIC>
-__global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(FusedArgs a) {
+__global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const Problem& p = a.p;
@@ -497,6 +528,11 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
   for (int j = 0; j < NS; ++j) tok[j] = utt_token(p, b, lane * NS + j, L);
   const int tok_left = utt_token(p, b, lane * NS - 1, L);
 
+  long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  (void)tm;
+#ifdef CTCB200_FUSED_TIMING
+  const long long t_start = clock64();
+#endif
   // recursion state (only meaningful in the two recursion warps)
   float v0[NS], v1[NS];
   double c = 0.0;
@@ -515,14 +551,20 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
   }
 
   // ------------------------------------------------ phase A ------------------------------------------------------------
-  if (side == 0) {
-    if (role == 0) rec_phase<NS, CLASSIC, 0, false>(a, f, sv, b, M, 0, +1, v0, v1, c, lb, lane);
-    else worker_phase<NS, CLASSIC, 0, false>(a, f, sv, b, role - 1, M, 0, +1, L, 0.0, dl, tok, tok_left, lane);
-  } else {
-    if (role == 0) rec_phase<NS, CLASSIC, 1, false>(a, f, sv, b, n_t - M, n_t - 1, -1, v0, v1, c, lb, lane);
-    else worker_phase<NS, CLASSIC, 1, false>(a, f, sv, b, role - 1, n_t - M, n_t - 1, -1, L, 0.0, dl, tok, tok_left, lane);
+  {
+    const int cnt = (side == 0) ? M : n_t - M, tf = (side == 0) ? 0 : n_t - 1, ts = (side == 0) ? 1 : -1;
+    if (role == 0) {
+      if (side == 0) rec_phase<NS, CLASSIC, 0, false>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
+      else rec_phase<NS, CLASSIC, 1, false>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
+    } else {
+      worker_phase<NS, CLASSIC, false>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, tok_left, lane, tm);
+    }
   }
 
+#ifdef CTCB200_FUSED_TIMING
+  tm[0] = clock64() - t_start;
+  const long long t_mid = clock64();
+#endif
   // ------------------------------------------------ the middle ---------------------------------------------------------
   if (role == 0) {
     float* dst = xch + side * (S * kUpad);
@@ -544,15 +586,20 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
 
   // ------------------------------------------------ phase B ------------------------------------------------------------
   if (!dead) {
-    if (side == 0) {
-      if (role == 0) rec_phase<NS, CLASSIC, 0, true>(a, f, sv, b, n_t - M, M, +1, v0, v1, c, lb, lane);
-      else worker_phase<NS, CLASSIC, 0, true>(a, f, sv, b, role - 1, n_t - M, M, +1, L, lossd_mid, dl, tok, tok_left, lane);
+    const int cnt = (side == 0) ? n_t - M : M, tf = (side == 0) ? M : M - 1, ts = (side == 0) ? 1 : -1;
+    if (role == 0) {
+      if (side == 0) rec_phase<NS, CLASSIC, 0, true>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
+      else rec_phase<NS, CLASSIC, 1, true>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
     } else {
-      if (role == 0) rec_phase<NS, CLASSIC, 1, true>(a, f, sv, b, M, M - 1, -1, v0, v1, c, lb, lane);
-      else worker_phase<NS, CLASSIC, 1, true>(a, f, sv, b, role - 1, M, M - 1, -1, L, lossd_mid, dl, tok, tok_left, lane);
+      worker_phase<NS, CLASSIC, true>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, tok_left, lane, tm);
     }
   }
 
+#ifdef CTCB200_FUSED_TIMING
+  tm[1] = clock64() - t_mid;
+  if (a.dbg != nullptr && lane == 0)
+    for (int q = 0; q < 8; ++q) a.dbg[((size_t)b * (2 * (W + 1)) + warp) * 8 + q] = tm[q];
+#endif
   // ------------------------------------------------ loss and the rows nobody owns --------------------------------------
   if (side == 0 && role == 0) {
     // loss = -alpha[T, label_length] (classic_ctc_loss.py:152-165 / simplified_ctc_loss.py:73-83); frames beyond n_t
@@ -578,6 +625,17 @@ constexpr int kSmemPerSm = 227 * 1024;
 static bool fused_pick(const Problem& p, int* W, int* SL) {
   *W = 0; *SL = 0;
   if ((p.V & 3) != 0 || p.NS > kMaxNS) return false;
+  // developer override for experiments: CTCB200_FUSED_W / CTCB200_FUSED_SL
+  const char* ew = getenv("CTCB200_FUSED_W");
+  const char* es = getenv("CTCB200_FUSED_SL");
+  if (ew != nullptr && es != nullptr) {
+    const int w = atoi(ew), sl = atoi(es);
+    if (w >= 1 && w <= kMaxWorkers && sl >= 2 && sl <= kMaxRowSlots &&
+        fused_layout(p.V, p.Upad, p.S, w, sl).total <= kSmemPerSm) {
+      *W = w; *SL = sl;
+      return true;
+    }
+  }
   static const int cand[5][2] = {{3, 3}, {3, 2}, {2, 3}, {2, 2}, {1, 2}};
   const int budgets[2] = {kSmemPerSm / 2 - 1024, kSmemPerSm};
   for (int bi = 0; bi < 2; ++bi)
@@ -615,6 +673,10 @@ cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss
   a.d_loss = d_loss;
   a.loss = loss;
   a.grad = grad;
+  a.dbg = nullptr;
+#ifdef CTCB200_FUSED_TIMING
+  a.dbg = reinterpret_cast<long long*>(s.betaT);   // the staged path's beta scratch is unused by the fused kernel
+#endif
   fused_pick(p, &a.W, &a.SL);
   (void)W;
   const bool classic = p.variant == CTCB200_CLASSIC;
