@@ -38,10 +38,19 @@ __device__ __forceinline__ float lse2(float a, float b) {
   return fmaf(lg2_approx(1.0f + ex2_approx(t)), 0.6931471805599453f, fmaxf(a, b));
 }
 
+// warp-wide float max in one REDUX: floats are mapped monotonically to signed integers (flip the magnitude bits of
+// negatives), reduced with redux.sync.max.s32 and mapped back; -inf/+inf keep their order, NaN inputs are don't-care.
 __device__ __forceinline__ float warp_max(float v) {
+#ifdef CTCB200_SHUFFLE_MAX
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
   return v;
+#endif
+  int i = __float_as_int(v);
+  i ^= (i >> 31) & 0x7fffffff;
+  i = __reduce_max_sync(kFull, i);
+  i ^= (i >> 31) & 0x7fffffff;
+  return __int_as_float(i);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -76,8 +76,13 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void spin_until(const unsigned* p, unsigned need) {
   if (ld_acquire(p) >= need) return;
+#ifndef CTCB200_SPIN_MAXNS
+#define CTCB200_SPIN_MAXNS 20
+#endif
+  unsigned ns = 20;       // back-off: a waiting warp must not eat the issue slots of the warps it waits for
   do {
-    __nanosleep(20);      // back off: a waiting warp must not eat the issue slots of the warps it is waiting for
+    __nanosleep(ns);
+    if (ns < CTCB200_SPIN_MAXNS) ns <<= 1;
   } while (ld_acquire(p) < need);
 }
 // 1-D TMA store: shared -> global bulk copy tracked by the per-thread bulk async-group
@@ -462,15 +467,19 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           if (!((tp != p.blank) && (tp >= 0) && (tp < V))) occ_stay[j] = 0.0f;
         }
       }
-      // scatter first (needs no reduction), then the blank column: h + logsumexp_l(x[l])
+      // Scatter the occupancies into the row: row[token] -= d_loss * occ.
+      if (CLASSIC) {   // the horizontal (stay) occupancy of state l+1 re-emits label[l]: same target as state l's move
+        float s_next = __shfl_down_sync(kFull, occ_stay[0], 1);
+        if (lane == 31) s_next = 0.0f;
 #pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        if (occ[j] > 0.0f) atomicAdd(&row[tok[j]], -dl * occ[j]);
-        if (CLASSIC) {
-          const int tp = (j > 0) ? tok[j - 1] : tok_left;
-          if (occ_stay[j] > 0.0f) atomicAdd(&row[tp], -dl * occ_stay[j]);
-        }
+        for (int j = 0; j < NS; ++j) occ[j] += (j < NS - 1) ? occ_stay[j + 1] : s_next;
       }
+      // (shared-memory float atomics: measured faster on B200 than a shuffle-combined or conflict-mask-guarded plain
+      // read-modify-write)
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+        if (occ[j] > 0.0f) atomicAdd(&row[tok[j]], -dl * occ[j]);
+      __syncwarp();
       const float XM = warp_max(xm);
       const float XM0 = (XM == kNegInf) ? 0.0f : XM;
       float xs = 0.0f;
@@ -478,7 +487,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       for (int j = 0; j < NS; ++j) xs += ex2_approx((x[j] - XM0) * kLog2e);
       xs = warp_sum(xs);
       const float occ_blank = (XM == kNegInf) ? 0.0f : __expf(K + (h + (XM + __logf(xs))));
-      if (lane == 0) atomicAdd(&row[p.blank], -dl * occ_blank);
+      if (lane == 0) row[p.blank] -= dl * occ_blank;
       __syncwarp();
       if (lane == 0) {
         fence_proxy_async();                                    // generic-proxy writes -> visible to the TMA store
@@ -495,7 +504,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
 template <int NS, bool CLASSIC>
-__global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
+__global__ void __launch_bounds__(2 * ((CLASSIC ? 3 : kMaxWorkers) + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const Problem& p = a.p;
@@ -630,16 +639,18 @@ static bool fused_pick(const Problem& p, int* W, int* SL) {
   const char* es = getenv("CTCB200_FUSED_SL");
   if (ew != nullptr && es != nullptr) {
     const int w = atoi(ew), sl = atoi(es);
-    if (w >= 1 && w <= kMaxWorkers && sl >= 2 && sl <= kMaxRowSlots &&
+    if (w >= 1 && w <= (p.S == 2 ? 3 : kMaxWorkers) && sl >= 2 && sl <= kMaxRowSlots &&
         fused_layout(p.V, p.Upad, p.S, w, sl).total <= kSmemPerSm) {
       *W = w; *SL = sl;
       return true;
     }
   }
-  static const int cand[5][2] = {{3, 3}, {3, 2}, {2, 3}, {2, 2}, {1, 2}};
+  // measured on B200 (cfg B=256 T=1000 V=1024): 4 workers x 2 buffers beats 3 x 3; the classic variant keeps 3 workers
+  // because its recursion warps need the 128-register budget of a 256-thread CTA.
+  static const int cand[6][2] = {{4, 2}, {3, 3}, {3, 2}, {2, 3}, {2, 2}, {1, 2}};
   const int budgets[2] = {kSmemPerSm / 2 - 1024, kSmemPerSm};
   for (int bi = 0; bi < 2; ++bi)
-    for (int c = 0; c < 5; ++c)
+    for (int c = (p.S == 2 ? 1 : 0); c < 6; ++c)
       if (fused_layout(p.V, p.Upad, p.S, cand[c][0], cand[c][1]).total <= budgets[bi]) {
         *W = cand[c][0]; *SL = cand[c][1];
         return true;
