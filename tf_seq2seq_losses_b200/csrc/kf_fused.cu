@@ -47,6 +47,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {   // release at CTA scope
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   unsigned done;
   do {
@@ -136,7 +139,7 @@ __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int 
   f.off_xoff = o; o += 2 * 8;
   o = fl_align(o, 128);
   int s = 0;
-  f.s_ctl = s;   s += fl_align((2 * W + 2) * 4, 16);          // dcount[W], done[W], ccount, scount
+  f.s_ctl = s;   s += 3 * f.R * 8;                            // ring barriers: full_d[R], full_s[R], empty[R]
   f.s_bar = s;   s += W * kMaxRowSlots * 8;
   s = fl_align(s, 128);
   f.s_row = s;   s += W * SL * V * 4;
@@ -166,10 +169,12 @@ struct FusedArgs {
 
 // view of one side's shared memory
 struct SideView {
-  unsigned* dcount;   // [W] rows whose ring inputs each worker has published
-  unsigned* done;     // [W] rows each worker has completely finished (phase B)
-  unsigned* ccount;   // frames the recursion warp has consumed
-  unsigned* scount;   // frames whose pre-step state the recursion warp has published (phase B)
+  // Ring hand-off barriers (mbarriers, arrival count 1; a waiting warp is suspended by the hardware instead of
+  // spinning on an issue slot).  The k-th use of ring slot q completes phase k of its barriers.
+  unsigned long long* full_d;   // [R] worker -> recursion: the frame's inputs (h, d[.]) are in the ring slot
+  unsigned long long* full_s;   // [R] recursion -> worker (phase B): the pre-step state of the frame is in the ring slot
+  unsigned long long* empty;    // [R] slot released: by the recursion once it has read the inputs (phase A), by the
+                                //     worker once the frame's gradient row is finished (phase B)
   unsigned long long* bar;   // [W][kMaxRowSlots]
   float* row;         // [W][SL][V]
   float* ringd;       // [R][Upad]
@@ -182,11 +187,10 @@ struct SideView {
 __device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLayout& f, int side) {
   unsigned char* base = smem + f.off_side0 + side * f.side_bytes;
   SideView v;
-  unsigned* ctl = reinterpret_cast<unsigned*>(base + f.s_ctl);
-  v.dcount = ctl;
-  v.done = ctl + f.W;
-  v.ccount = ctl + 2 * f.W;
-  v.scount = ctl + 2 * f.W + 1;
+  unsigned long long* ctl = reinterpret_cast<unsigned long long*>(base + f.s_ctl);
+  v.full_d = ctl;
+  v.full_s = ctl + f.R;
+  v.empty = ctl + 2 * f.R;
   v.bar = reinterpret_cast<unsigned long long*>(base + f.s_bar);
   v.row = reinterpret_cast<float*>(base + f.s_row);
   v.ringd = reinterpret_cast<float*>(base + f.s_ringd);
@@ -210,11 +214,10 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
                                           int t_first, int t_step, float* v0, float* v1, double& c,
                                           const LabelBits<NS>& lb, int lane, long long* tm) {
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
-  const int W = f.W, R = f.R;
+  const int R = f.R;
   float m_pend = kNegInf;
-  int w = 0, n = 0;            // worker / row of frame i
   int slot = 0;                // i % R
-  int wj = 0, nj = 0;          // worker / row of frame i - R (phase B back-pressure)
+  unsigned use_par = 0;        // (i / R) & 1: parity of this use of the slot
   float* g_state = a.stateT + ((size_t)b * a.p.T + t_first) * (size_t)(S * kUpad);
   double* g_off = a.coff + (size_t)b * a.p.T + t_first;
   const ptrdiff_t g_step = (ptrdiff_t)t_step * (S * kUpad);
@@ -223,7 +226,7 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
     for (int k = 0; k < kFusedGroup; ++k) {
       const int i = i0 + k;
       if (i < count) {
-        TIMED(3, spin_until(sv.dcount + w, (unsigned)(n + 1)));   // the frame's inputs are in the ring
+        TIMED(3, mbar_wait(sv.full_d + slot, use_par));          // the frame's inputs are in the ring
         float d[NS];
         const float* dsrc = sv.ringd + slot * kUpad;
 #pragma unroll
@@ -231,7 +234,7 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
         const float h = sv.ringh[slot];
         if (!PHASE_B) {
           __syncwarp();
-          if (lane == 0) st_release(sv.ccount, (unsigned)(i + 1));   // ring slot may be refilled
+          if (lane == 0) mbar_arrive(sv.empty + slot);             // ring slot may be refilled
           // pre-step state -> global scratch for the other side's phase B
 #pragma unroll
           for (int j = 0; j < NS; ++j) {
@@ -242,10 +245,7 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
           g_state += g_step;
           g_off += t_step;
         } else {
-          if (i >= R) {                                          // the state slot's previous frame is fully processed
-            TIMED(6, spin_until(sv.done + wj, (unsigned)(nj + 1)));
-            if (++wj == W) { wj = 0; ++nj; }
-          }
+          if (i >= R) TIMED(6, mbar_wait(sv.empty + slot, use_par ^ 1u));   // previous frame of the slot is finished
           float* dst = sv.rings + slot * (S * kUpad);
 #pragma unroll
           for (int j = 0; j < NS; ++j) {
@@ -254,7 +254,7 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
           }
           if (lane == 0) sv.ringc[slot] = c;
           __syncwarp();
-          if (lane == 0) st_release(sv.scount, (unsigned)(i + 1));
+          if (lane == 0) mbar_arrive(sv.full_s + slot);
         }
         if (SIDE == 0) {
           if (CLASSIC) alpha_step_classic<NS>(v0, v1, d, h, lane, lb);
@@ -265,8 +265,7 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
         }
         if (k == 0) m_pend = state_max<NS, CLASSIC>(v0, v1);
         if (k == 2) apply_offset<NS, CLASSIC>(v0, v1, m_pend, c);
-        if (++w == W) { w = 0; ++n; }
-        if (++slot == R) slot = 0;
+        if (++slot == R) { slot = 0; use_par ^= 1u; }
       }
     }
   }
@@ -300,6 +299,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       bulk_load(rowbuf + (size_t)q * V, logits_b + (size_t)(t_first + (w + q * W) * t_step) * V, row_bytes, bars + q);
     }
   int slot = w % R;        // ring slot of frame i = w + n*W
+  unsigned use_par = 0;    // (i / R) & 1
   int rs = 0;              // row buffer of row n (= n % SL)
   unsigned par = 0;        // bit q: parity of the next completion to wait for on row buffer q
   // scalars of the row produced in phase A, fetched one row ahead (plain loads: written by this CTA in phase A)
@@ -368,7 +368,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       lse = M0 + logf(sum);
       if (lane == 0) a.rowlse[(size_t)b * p.T + t] = lse;
     }
-    if (!PHASE_B && i >= R) TIMED(4, spin_until(sv.ccount, (unsigned)(i - R + 1)));   // ring slot consumed by the recursion
+    if (!PHASE_B && i >= R) TIMED(4, mbar_wait(sv.empty + slot, use_par ^ 1u));   // slot consumed by the recursion
     float dd[NS];
     {
       float* dst = sv.ringd + slot * kUpad;
@@ -383,7 +383,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     const float h = row[p.blank] - lse;
     if (lane == 0) sv.ringh[slot] = h;
     __syncwarp();
-    if (lane == 0) st_release(sv.dcount + w, (unsigned)(n + 1));
+    if (lane == 0) mbar_arrive(sv.full_d + slot);
 
     // ---- stage 1b (phase B): the dense softmax part of the gradient row, in place, while the recursion catches up.
     // d loss/d logit = d_loss * (softmax * sum_k occ - occ); sum_k occ is 1 for every frame of a feasible sample (it is
@@ -411,7 +411,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 
     // ---- stage 2 (phase B): occupancies of the frame, scattered into the row; then the row leaves by TMA ----
     if (PHASE_B) {
-      TIMED(5, spin_until(sv.scount, (unsigned)(i + 1)));      // the running side's state for this frame is published
+      TIMED(5, mbar_wait(sv.full_s + slot, use_par));          // the running side's state for this frame is published
       TIMED(7, fused_cp_async_wait_all());
       __syncwarp();
       const float* ring_state = sv.rings + slot * (S * kUpad);
@@ -492,11 +492,11 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       if (lane == 0) {
         fence_proxy_async();                                    // generic-proxy writes -> visible to the TMA store
         bulk_store(a.grad + ((size_t)b * p.T + t) * V, row, row_bytes);
-        st_release(sv.done + w, (unsigned)(n + 1));             // state-ring slot and stb are free again
+        mbar_arrive(sv.empty + slot);                          // ring slot and stb are free again
       }
     }
     slot += W;
-    if (slot >= R) slot -= R;
+    if (slot >= R) { slot -= R; use_par ^= 1u; }
     if (++rs == SL) rs = 0;
   }
   if (PHASE_B && lane == 0) bulk_store_wait_read();             // shared memory must outlive the stores reading it
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(2 * ((CLASSIC ? 3 : kMaxWorkers) + 1) * kWarp,
   auto reset_sync_state = [&]() {     // one thread: counters to zero, mbarriers to phase 0
     for (int s2 = 0; s2 < 2; ++s2) {
       const SideView v = side_view(smem, f, s2);
-      for (int k = 0; k < 2 * W + 2; ++k) v.dcount[k] = 0u;
+      for (int k = 0; k < 3 * f.R; ++k) mbar_init(v.full_d + k, 1u);
       for (int k = 0; k < W * kMaxRowSlots; ++k) mbar_init(v.bar + k, 1u);
     }
     fence_mbar_init();
