@@ -262,8 +262,18 @@ def main():
     else:
         dom, dom_ms = "whole call", ms_step
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json), if this
+    # workload / kernel was captured
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = f"{args.workload}:{variant}:{dom}"
+        if key in tr and local_B == B and not args.ragged:
+            traffic = tr[key]["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": dom_ms, "stage_ms": stage_ms,
                 "path_achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "path_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak}
 

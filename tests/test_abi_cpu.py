@@ -1,0 +1,82 @@
+"""CPU-only checks of the C-ABI shared library and the host layer: the library loads without a GPU, exports every
+symbol include/ctc_b200.h declares, validates descriptors, and the Python face refuses to run without CUDA (there is
+no CPU fallback).  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from tf_seq2seq_losses_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ctc_b200.h")).read()
+    return sorted(set(re.findall(r"\b(ctcb200_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), f"libctc_b200.so does not export {name}"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    assert lib.ctcb200_version() == 100
+
+
+def test_error_strings_and_descriptor_validation():
+    lib = _lib.load()
+    assert lib.ctcb200_strerror(0) == b"ok"
+    for code in range(-6, 0):
+        assert lib.ctcb200_strerror(code) not in (b"ok", b"unknown error")
+    good = _lib.Desc(4, 10, 8, 3, 0, _lib.CLASSIC, 4, 0)
+    assert lib.ctcb200_workspace_bytes(ctypes.byref(good), _lib.WS_LOSS_GRAD) > 0
+    assert lib.ctcb200_workspace_bytes(ctypes.byref(good), _lib.WS_HESSIAN) > lib.ctcb200_workspace_bytes(
+        ctypes.byref(good), _lib.WS_LOSS_GRAD)
+    for bad in (_lib.Desc(-1, 10, 8, 3, 0, 0, 4, 0),      # negative batch
+                _lib.Desc(4, 10, 8, 3, 8, 0, 4, 0),       # blank out of range
+                _lib.Desc(4, 10, 8, 3, 0, 2, 4, 0),       # unknown variant
+                _lib.Desc(4, 10, 8, 3, 0, 0, 4, 1 << 20),  # unknown flag
+                _lib.Desc(4, 1000, 8, 600, 0, 0, 601, 0),  # more than 512 label states
+                _lib.Desc(4, 10, 40000, 3, 0, 0, 4, 0)):   # more than 32768 tokens
+        assert lib.ctcb200_workspace_bytes(ctypes.byref(bad), _lib.WS_LOSS_GRAD) == 0
+    # null pointers and a too-small workspace are reported, not dereferenced
+    vp = ctypes.c_void_p
+    assert lib.ctcb200_loss_grad(ctypes.byref(good), None, None, None, None, None, None, None, None, None, 0, None) == -1
+    buf = (ctypes.c_char * 512)()
+    p = ctypes.cast(buf, vp)
+    aligned = vp((p.value + 255) & ~255)
+    assert lib.ctcb200_loss_grad(ctypes.byref(good), aligned, aligned, aligned, aligned, None, aligned, aligned, None,
+                                 vp(aligned.value + 4), 1 << 30, None) == -6    # misaligned workspace
+    assert lib.ctcb200_loss_grad(ctypes.byref(good), aligned, aligned, aligned, aligned, None, aligned, aligned, None,
+                                 aligned, 16, None) == -3                        # workspace too small
+    # stage names: the fused kernel takes V % 4 == 0, the staged kernels everything else
+    assert lib.ctcb200_stage_names(ctypes.byref(good)) == b"kf_fused"
+    odd = _lib.Desc(4, 10, 29, 3, 0, _lib.CLASSIC, 4, 0)
+    assert lib.ctcb200_stage_names(ctypes.byref(odd)) == b"k1_softmax_gather,k2_recursion,k3_grad"
+    assert lib.ctcb200_launches_per_call(ctypes.byref(good)) == 1 and lib.ctcb200_launches_per_call(ctypes.byref(odd)) == 3
+
+
+def test_python_face_has_no_cpu_fallback():
+    import tf_seq2seq_losses_b200 as pkg
+    logits = torch.zeros((1, 4, 3))
+    with pytest.raises(_lib.CtcB200Error):
+        pkg.classic_ctc_loss(torch.ones((1, 2), dtype=torch.int32), logits, torch.tensor([2]), torch.tensor([4]), 0)
+    with pytest.raises(_lib.CtcB200Error):
+        pkg.simple_ctc_loss(torch.ones((1, 2), dtype=torch.int32), logits, torch.tensor([2]), torch.tensor([4]), 0)
+    with pytest.raises(AssertionError):       # rank / dtype checks of tf_seq2seq_losses/base_loss.py:129-138
+        pkg.classic_ctc_loss(torch.ones((1, 2), dtype=torch.int32), logits.double(), torch.tensor([2]), torch.tensor([4]), 0)
+    assert pkg.simple_ctc_loss is pkg.simplified_ctc_loss
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "tf_seq2seq_losses_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                text = open(os.path.join(dirpath, name)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "ctc_oracle" not in text, name
