@@ -35,6 +35,9 @@ namespace ctcb200 {
 
 constexpr int kMaxRowSlots = 3;     // TMA row buffers per worker: current + prefetch (+ one draining its TMA store)
 constexpr int kFusedGroup = 4;      // frames per unrolled group (renormalisation cadence, see recursion.cuh)
+#ifndef CTCB200_L2_PREFETCH_ROWS
+#define CTCB200_L2_PREFETCH_ROWS 0  // rows (per worker) requested into L2 ahead of the shared-memory load; measured on B200: 2/4/8 rows make the kernel 6/20/33% slower, so it is off
+#endif
 constexpr int kMaxWorkers = 4;
 
 // ---- PTX helpers -----------------------------------------------------------------------------------------------
@@ -68,6 +71,10 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsi
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// TMA prefetch of a global range into L2: deepens the HBM pipeline without spending shared memory on more row buffers
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -292,7 +299,10 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   const float* rowlse_b = a.rowlse + (size_t)b * p.T;
   const double* coff_b = a.coff + (size_t)b * p.T;
 
-  // prologue: the first SL-1 rows are in flight before any is consumed
+  // prologue: the first SL-1 rows are in flight before any is consumed, the next few are on their way into L2
+  if (lane == 0)
+    for (int q = SL - 1; q < SL - 1 + CTCB200_L2_PREFETCH_ROWS && q < n_my; ++q)
+      bulk_prefetch_l2(logits_b + (size_t)(t_first + (w + q * W) * t_step) * V, row_bytes);
   if (lane == 0)
     for (int q = 0; q < SL - 1 && q < n_my; ++q) {
       mbar_expect_tx(bars + q, row_bytes);
@@ -330,6 +340,15 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
         cst_next = coff_b[tn];
       }
     }
+    // ---- prefetch (phase A): the buffer row n-1 used is free as soon as this iteration starts ----
+    if (!PHASE_B && lane == 0 && n + SL - 1 < n_my) {
+      const int q = (rs == 0) ? SL - 1 : rs - 1;
+      fence_proxy_async();
+      mbar_expect_tx(bars + q, row_bytes);
+      bulk_load(rowbuf + (size_t)q * V, logits_b + (size_t)(t + (SL - 1) * W * t_step) * V, row_bytes, bars + q);
+    }
+    if (lane == 0 && n + SL - 1 + CTCB200_L2_PREFETCH_ROWS < n_my)
+      bulk_prefetch_l2(logits_b + (size_t)(t + (SL - 1 + CTCB200_L2_PREFETCH_ROWS) * W * t_step) * V, row_bytes);
     TIMED(2, mbar_wait(bars + rs, (par >> rs) & 1u));          // the row has landed
     par ^= 1u << rs;
     float* row = rowbuf + (size_t)rs * V;
@@ -400,10 +419,11 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       }
     }
 
-    // ---- prefetch: row n+SL-1 goes into the buffer row n-1 used; its TMA store (phase B) must have drained ----
-    if (lane == 0 && n + SL - 1 < n_my) {
+    // ---- prefetch (phase B): row n+SL-1 goes into the buffer row n-1 used; its TMA store must have drained first,
+    // which is why this sits after the softmax pass rather than at the top of the iteration ----
+    if (PHASE_B && lane == 0 && n + SL - 1 < n_my) {
       const int q = (rs == 0) ? SL - 1 : rs - 1;
-      if (PHASE_B) bulk_store_wait_read();
+      bulk_store_wait_read();
       fence_proxy_async();
       mbar_expect_tx(bars + q, row_bytes);
       bulk_load(rowbuf + (size_t)q * V, logits_b + (size_t)(t + (SL - 1) * W * t_step) * V, row_bytes, bars + q);

@@ -36,7 +36,7 @@ NS = (L + 1 + 31) // 32
 Upad = 32 * NS
 rows, srows = B * T, B * (T + 1) * S * Upad
 off = a256(rows * 4) * 2 + a256(rows * Upad * 4) + a256(srows * 4)       # byte offset of the beta scratch
-W = 3
+W = int(os.environ.get("CTCB200_FUSED_W", "4" if variant == _lib.SIMPLIFIED else "3"))
 warps = 2 * (W + 1)
 dbg = ws[off: off + B * warps * 8 * 8].view(torch.int64).reshape(B, warps, 8).cpu().numpy().astype(np.float64)
 names = ["phaseA", "phaseB", "tma_wait", "dcount_wait", "ccount_wait", "scount_wait", "done_wait", "state_cpasync_wait"]
