@@ -54,11 +54,11 @@ def test_error_strings_and_descriptor_validation():
                                  vp(aligned.value + 4), 1 << 30, None) == -6    # misaligned workspace
     assert lib.ctcb200_loss_grad(ctypes.byref(good), aligned, aligned, aligned, aligned, None, aligned, aligned, None,
                                  aligned, 16, None) == -3                        # workspace too small
-    # stage names: the fused kernel takes V % 4 == 0, the staged kernels everything else
+    # stage names: one fused launch by default, the three staged kernels on request
     assert lib.ctcb200_stage_names(ctypes.byref(good)) == b"kf_fused"
-    odd = _lib.Desc(4, 10, 29, 3, 0, _lib.CLASSIC, 4, 0)
-    assert lib.ctcb200_stage_names(ctypes.byref(odd)) == b"k1_softmax_gather,k2_recursion,k3_grad"
-    assert lib.ctcb200_launches_per_call(ctypes.byref(good)) == 1 and lib.ctcb200_launches_per_call(ctypes.byref(odd)) == 3
+    staged = _lib.Desc(4, 10, 29, 3, 0, _lib.CLASSIC, 4, _lib.FORCE_STAGED)
+    assert lib.ctcb200_stage_names(ctypes.byref(staged)) == b"k1_softmax_gather,k2_recursion,k3_grad"
+    assert lib.ctcb200_launches_per_call(ctypes.byref(good)) == 1 and lib.ctcb200_launches_per_call(ctypes.byref(staged)) == 3
 
 
 def test_python_face_has_no_cpu_fallback():

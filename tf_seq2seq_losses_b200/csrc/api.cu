@@ -104,8 +104,8 @@ const char* ctcb200_strerror(int code) {
   }
 }
 
-// The fused kernel takes the loss+gradient call whenever the shape allows (V % 4 == 0 for the 16-byte TMA rows and the
-// shared-memory plan fits); pointer alignment is checked per call.
+// The fused kernel takes the loss+gradient call whenever its shared-memory plan fits (rows move by TMA when V % 4 == 0
+// and the bases are 16-byte aligned, by 4-byte cp.async otherwise).
 static int fused_workers(const ctcb200_desc* desc, const Problem& p) {
   if (desc->flags & CTCB200_FORCE_STAGED) return 0;
   return fused_pick_workers(p);
@@ -143,8 +143,7 @@ int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* loss_out = loss ? loss : s.loss;
   const int W = fused_workers(desc, p);
-  if (W > 0 && grad_logits != nullptr && grad_logprobas == nullptr && p.T > 0 &&
-      ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(grad_logits)) & 15) == 0) {
+  if (W > 0 && grad_logits != nullptr && grad_logprobas == nullptr && p.T > 0) {
     CTCB200_CUDA(launch_fused(p, s, d_loss, loss_out, grad_logits, W, st));
     return CTCB200_OK;
   }

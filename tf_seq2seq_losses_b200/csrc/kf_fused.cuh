@@ -1,0 +1,733 @@
+// KF: the fused loss + d/dlogits kernel -- ONE launch for the whole hot path, one CTA per utterance.
+//
+// What it replaces in the reference: the log-softmax (tf_seq2seq_losses/tools.py:27-40), the label-state gathers
+// (base_loss.py:328-418), the alpha/beta tf.while_loop recursions (classic_ctc_loss.py:310-462,
+// simplified_ctc_loss.py:291-438), the loss read-out, _combine_transition_probabilities with its token scatter
+// (classic_ctc_loss.py:565-669, simplified_ctc_loss.py:456-534, base_loss.py:420-468), the gradient
+// (base_loss.py:262-298) and TF's autodiff of the log-softmax -- i.e. everything the staged kernels K1+K2+K3 do, with
+// the [B,T,U] gathered-probability scratch and one of the two state tensors never leaving the SM.
+//
+// Schedule ("meet in the middle").  For an utterance with n frames, M = n/2:
+//   phase A  alpha runs forward over frames 0..M-1 while beta runs backward over frames n-1..M.  Each side stores the
+//            state it held *before* consuming a frame (alpha[t] for t < M, beta[t+1] for t >= M) to global scratch.
+//   middle   logZ = logsumexp_l(alpha[M,l] + beta[M,l]) -- the normaliser every occupancy needs -- is known half-way.
+//   phase B  alpha continues over frames M..n-1 and beta over M-1..0.  At frame t the running side's state and the
+//            other side's stored state give the occupancies of that frame, and the gradient row is written at once.
+// Every logits row is therefore read twice (once per phase) and every gradient row written once; the serial chain is
+// n/2 + n/2 steps instead of 2n.
+//
+// Warp roles (per side s in {alpha, beta}; W row workers per side):
+//   recursion warp   NS states per lane in registers, one shuffle per frame (recursion.cuh); consumes per-frame
+//                    inputs (h, d[.]) from a shared-memory ring and publishes its pre-step state.
+//   row workers      each owns whole logits rows: a 1-D TMA bulk copy (cp.async.bulk + mbarrier complete_tx) lands the
+//                    row in shared memory (double buffered), the warp reduces it (phase A: row log-sum-exp), gathers
+//                    the <= U label columns into the ring, and in phase B combines alpha*beta into per-token
+//                    occupancies (occupancy.cuh) and streams out the dense gradient row with 128-bit stores.
+// Warps hand work to each other through monotonic counters in shared memory (st.release / ld.acquire at CTA scope);
+// there is no CTA-wide barrier inside a phase.
+#pragma once
+#include <cstdlib>
+
+#include "common.cuh"
+#include "occupancy.cuh"
+#include "recursion.cuh"
+
+namespace ctcb200 {
+
+constexpr int kMaxRowSlots = 3;     // TMA row buffers per worker: current + prefetch (+ one draining its TMA store)
+constexpr int kFusedGroup = 4;      // frames per unrolled group (renormalisation cadence, see recursion.cuh)
+#ifndef CTCB200_L2_PREFETCH_ROWS
+#define CTCB200_L2_PREFETCH_ROWS 0  // rows (per worker) requested into L2 ahead of the shared-memory load; measured on B200: 2/4/8 rows make the kernel 6/20/33% slower, so it is off
+#endif
+constexpr int kMaxWorkers = 4;
+
+// ---- PTX helpers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {   // release at CTA scope
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D TMA: global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// TMA prefetch of a global range into L2: deepens the HBM pipeline without spending shared memory on more row buffers
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until(const unsigned* p, unsigned need) {
+  if (ld_acquire(p) >= need) return;
+#ifndef CTCB200_SPIN_MAXNS
+#define CTCB200_SPIN_MAXNS 20
+#endif
+  unsigned ns = 20;       // back-off: a waiting warp must not eat the issue slots of the warps it waits for
+  do {
+    __nanosleep(ns);
+    if (ns < CTCB200_SPIN_MAXNS) ns <<= 1;
+  } while (ld_acquire(p) < need);
+}
+// 1-D TMA store: shared -> global bulk copy tracked by the per-thread bulk async-group
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fused_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fused_cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fused_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fused_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2: two lanes of fp32 per issue slot) -----------------------------
+// exp((v - m)) for the four elements of a float4, as 2^((v - m) * log2e): subtract first (exact for |v| ~ 1e10), then
+// scale -- both as packed ops -- then four MUFU.EX2.
+__device__ __forceinline__ float4 exp4_shifted(float4 v, float m) {
+  const float2 nm = make_float2(-m, -m), k = make_float2(1.4426950408889634f, 1.4426950408889634f);
+  const float2 lo = __fmul2_rn(__fadd2_rn(make_float2(v.x, v.y), nm), k);
+  const float2 hi = __fmul2_rn(__fadd2_rn(make_float2(v.z, v.w), nm), k);
+  return make_float4(ex2_approx(lo.x), ex2_approx(lo.y), ex2_approx(hi.x), ex2_approx(hi.y));
+}
+__device__ __forceinline__ float hsum4(float4 e) {
+  const float2 s = __fadd2_rn(make_float2(e.x, e.y), make_float2(e.z, e.w));
+  return s.x + s.y;
+}
+
+// ---- optional wait-time instrumentation (compile with -DCTCB200_FUSED_TIMING; results go to FusedArgs::dbg) --------
+// per warp: [0] phase A cycles, [1] phase B cycles, [2] TMA wait, [3] dcount wait, [4] ccount wait, [5] scount wait,
+//           [6] done wait, [7] state cp.async wait
+#ifdef CTCB200_FUSED_TIMING
+#define TIMED(slot, stmt)                       \
+  do {                                          \
+    const long long t0__ = clock64();           \
+    stmt;                                       \
+    tm[slot] += clock64() - t0__;               \
+  } while (0)
+#else
+#define TIMED(slot, stmt) \
+  do {                    \
+    stmt;                 \
+  } while (0)
+#endif
+
+// ---- shared-memory layout (one definition for host sizing and device carving) ---------------------------------------
+struct FusedLayout {
+  int W, R, SL;             // workers per side, ring depth (= 2W, a multiple of W), row buffers per worker
+  int off_xch, off_xoff, off_side0, total;
+  // offsets inside a side block
+  int s_ctl, s_bar, s_row, s_ringd, s_ringh, s_rings, s_ringc, s_stbuf, side_bytes;
+};
+
+__host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL) {
+  FusedLayout f;
+  f.W = W;
+  f.R = 2 * W;
+  f.SL = SL;
+  int o = 0;
+  f.off_xch = o;  o += 2 * S * Upad * 4;
+  f.off_xoff = o; o += 2 * 8;
+  o = fl_align(o, 128);
+  int s = 0;
+  f.s_ctl = s;   s += 3 * f.R * 8;                            // ring barriers: full_d[R], full_s[R], empty[R]
+  f.s_bar = s;   s += W * kMaxRowSlots * 8;
+  s = fl_align(s, 128);
+  f.s_row = s;   s += W * SL * ((V + 3) & ~3) * 4;
+  f.s_ringd = s; s += f.R * Upad * 4;
+  f.s_ringh = s; s += fl_align(f.R * 4, 16);
+  f.s_rings = s; s += f.R * S * Upad * 4;
+  f.s_ringc = s; s += f.R * 8;
+  s = fl_align(s, 16);
+  f.s_stbuf = s; s += W * S * Upad * 4;
+  f.side_bytes = fl_align(s, 128);
+  f.off_side0 = o;
+  f.total = o + 2 * f.side_bytes;
+  return f;
+}
+
+struct FusedArgs {
+  Problem p;
+  float* rowlse;        // [B*T]          row log-sum-exp (phase A -> phase B)
+  float* stateT;        // [B*T*S*Upad]   row t: alpha[t] if t < M(b) else beta[t+1]; private layout
+  double* coff;         // [B*T]          renormalisation offset of that row
+  const float* d_loss;  // [B] or null
+  float* loss;          // [B]
+  float* grad;          // [B,T,V]
+  int W, SL;
+  int tma;              // 1: rows move by 1-D TMA (V % 4 == 0, 16-byte aligned bases); 0: by 4-byte cp.async / plain stores
+  long long* dbg;       // [B][warps][8] when built with CTCB200_FUSED_TIMING, else unused
+};
+
+// view of one side's shared memory
+struct SideView {
+  // Ring hand-off barriers (mbarriers, arrival count 1; a waiting warp is suspended by the hardware instead of
+  // spinning on an issue slot).  The k-th use of ring slot q completes phase k of its barriers.
+  unsigned long long* full_d;   // [R] worker -> recursion: the frame's inputs (h, d[.]) are in the ring slot
+  unsigned long long* full_s;   // [R] recursion -> worker (phase B): the pre-step state of the frame is in the ring slot
+  unsigned long long* empty;    // [R] slot released: by the recursion once it has read the inputs (phase A), by the
+                                //     worker once the frame's gradient row is finished (phase B)
+  unsigned long long* bar;   // [W][kMaxRowSlots]
+  float* row;         // [W][SL][V]
+  float* ringd;       // [R][Upad]
+  float* ringh;       // [R]
+  float* rings;       // [R][S*Upad]
+  double* ringc;      // [R]
+  float* stbuf;       // [W][S*Upad]
+};
+
+__device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLayout& f, int side) {
+  unsigned char* base = smem + f.off_side0 + side * f.side_bytes;
+  SideView v;
+  unsigned long long* ctl = reinterpret_cast<unsigned long long*>(base + f.s_ctl);
+  v.full_d = ctl;
+  v.full_s = ctl + f.R;
+  v.empty = ctl + 2 * f.R;
+  v.bar = reinterpret_cast<unsigned long long*>(base + f.s_bar);
+  v.row = reinterpret_cast<float*>(base + f.s_row);
+  v.ringd = reinterpret_cast<float*>(base + f.s_ringd);
+  v.ringh = reinterpret_cast<float*>(base + f.s_ringh);
+  v.rings = reinterpret_cast<float*>(base + f.s_rings);
+  v.ringc = reinterpret_cast<double*>(base + f.s_ringc);
+  v.stbuf = reinterpret_cast<float*>(base + f.s_stbuf);
+  return v;
+}
+
+__device__ __forceinline__ void fused_zero_row(float* dst, int V, int lane, bool vec) {
+  if (vec) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < (V >> 2); i += kWarp) stg_stream4(d4 + i, z);
+  } else {
+    for (int i = lane; i < V; i += kWarp) dst[i] = 0.0f;
+  }
+}
+
+// ---- recursion warp, one phase ---------------------------------------------------------------------------------------
+// Frame i of the phase is frame t = t_first + i * t_step of the utterance.  SIDE 0 = alpha (forward), 1 = beta.
+template <int NS, bool CLASSIC, int SIDE, bool PHASE_B>
+__device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int b, int count,
+                                          int t_first, int t_step, float* v0, float* v1, double& c,
+                                          const LabelBits<NS>& lb, int lane, long long* tm) {
+  constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
+  const int R = f.R;
+  float m_pend = kNegInf;
+  int slot = 0;                // i % R
+  unsigned use_par = 0;        // (i / R) & 1: parity of this use of the slot
+  float* g_state = a.stateT + ((size_t)b * a.p.T + t_first) * (size_t)(S * kUpad);
+  double* g_off = a.coff + (size_t)b * a.p.T + t_first;
+  const ptrdiff_t g_step = (ptrdiff_t)t_step * (S * kUpad);
+  for (int i0 = 0; i0 < count; i0 += kFusedGroup) {
+#pragma unroll
+    for (int k = 0; k < kFusedGroup; ++k) {
+      const int i = i0 + k;
+      if (i < count) {
+        TIMED(3, mbar_wait(sv.full_d + slot, use_par));          // the frame's inputs are in the ring
+        float d[NS];
+        const float* dsrc = sv.ringd + slot * kUpad;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) d[j] = dsrc[j * kWarp + lane];
+        const float h = sv.ringh[slot];
+        if (!PHASE_B) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sv.empty + slot);             // ring slot may be refilled
+          // pre-step state -> global scratch for the other side's phase B
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+            g_state[j * kWarp + lane] = v0[j];
+            if (CLASSIC) g_state[kUpad + j * kWarp + lane] = v1[j];
+          }
+          if (lane == 0) *g_off = c;
+          g_state += g_step;
+          g_off += t_step;
+        } else {
+          if (i >= R) TIMED(6, mbar_wait(sv.empty + slot, use_par ^ 1u));   // previous frame of the slot is finished
+          float* dst = sv.rings + slot * (S * kUpad);
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+            dst[j * kWarp + lane] = v0[j];
+            if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
+          }
+          if (lane == 0) sv.ringc[slot] = c;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sv.full_s + slot);
+        }
+        if (SIDE == 0) {
+          if (CLASSIC) alpha_step_classic<NS>(v0, v1, d, h, lane, lb);
+          else alpha_step_simplified<NS>(v0, d, h, lane);
+        } else {
+          if (CLASSIC) beta_step_classic<NS>(v0, v1, d, h, lane, lb);
+          else beta_step_simplified<NS>(v0, d, h, lane);
+        }
+        if (k == 0) m_pend = state_max<NS, CLASSIC>(v0, v1);
+        if (k == 2) apply_offset<NS, CLASSIC>(v0, v1, m_pend, c);
+        if (++slot == R) { slot = 0; use_par ^= 1u; }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long* bars_of(const SideView& sv, int w) { return sv.bar + w * kMaxRowSlots; }
+
+// ---- row worker, one phase -------------------------------------------------------------------------------------------
+// tok[j] = cleaned label (base_loss.py:395-418) of this lane's states l = lane*NS + j, tok_left = label of state
+// lane*NS - 1; they live in registers for the whole kernel.  `side` is a runtime argument (one code body for both
+// sides keeps the instruction footprint inside the instruction cache).
+template <int NS, bool CLASSIC, bool PHASE_B, bool TMA>
+__device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int side, int b,
+                                          int w, int count, int t_first, int t_step, int L, double lossd_mid, float dl,
+                                          const int (&tok)[NS], int tok_left, int lane, long long* tm) {
+  constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const Problem& p = a.p;
+  const int W = f.W, R = f.R, SL = f.SL, V = p.V, Vp = (V + 3) & ~3, n4 = Vp >> 2;
+  const int n_my = (count > w) ? (count - w + W - 1) / W : 0;
+  const unsigned row_bytes = (unsigned)V * 4u;
+  constexpr bool tma = TMA;
+  const float* logits_b = p.logits + (size_t)b * p.T * V;
+  float* rowbuf = sv.row + (size_t)w * SL * Vp;
+  // Brings logits row `t` into row buffer q; completion is signalled on bars[q] either by the TMA transaction count
+  // (one elected lane) or, when rows are not 16-byte aligned, by every lane's cp.async completion.
+  auto load_row = [&](int q, int t) {
+    float* dst = rowbuf + (size_t)q * Vp;
+    const float* src = logits_b + (size_t)t * V;
+    if (tma) {
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bars_of(sv, w) + q, row_bytes);
+        bulk_load(dst, src, row_bytes, bars_of(sv, w) + q);
+      }
+    } else {
+      for (int k = lane; k < V; k += kWarp) fused_cp_async4(dst + k, src + k);
+      cp_async_mbar_arrive(bars_of(sv, w) + q);
+    }
+  };
+  unsigned long long* bars = bars_of(sv, w);
+  float* stb = sv.stbuf + w * (S * kUpad);
+  const float* rowlse_b = a.rowlse + (size_t)b * p.T;
+  const double* coff_b = a.coff + (size_t)b * p.T;
+
+  // prologue: the first SL-1 rows are in flight before any is consumed, the next few are on their way into L2
+  if (tma && lane == 0)
+    for (int q = SL - 1; q < SL - 1 + CTCB200_L2_PREFETCH_ROWS && q < n_my; ++q)
+      bulk_prefetch_l2(logits_b + (size_t)(t_first + (w + q * W) * t_step) * V, row_bytes);
+  if (!tma)   // pad lanes of the (4-float aligned) row buffers never receive data: make them neutral once
+    for (int q = 0; q < SL; ++q)
+      for (int k = V + lane; k < Vp; k += kWarp) rowbuf[(size_t)q * Vp + k] = kNegInf;
+  for (int q = 0; q < SL - 1 && q < n_my; ++q) load_row(q, t_first + (w + q * W) * t_step);
+  int slot = w % R;        // ring slot of frame i = w + n*W
+  unsigned use_par = 0;    // (i / R) & 1
+  int rs = 0;              // row buffer of row n (= n % SL)
+  unsigned par = 0;        // bit q: parity of the next completion to wait for on row buffer q
+  // scalars of the row produced in phase A, fetched one row ahead (plain loads: written by this CTA in phase A)
+  float lse_next = 0.0f;
+  double cst_next = 0.0;
+  if (PHASE_B && n_my > 0) {
+    const int t0 = t_first + w * t_step;
+    if (!p.input_logprobas) lse_next = rowlse_b[t0];
+    cst_next = coff_b[t0];
+  }
+  for (int n = 0; n < n_my; ++n) {
+    const int i = w + n * W;
+    const int t = t_first + i * t_step;
+    float lse = lse_next;
+    const double cst = cst_next;
+    if (PHASE_B) {
+      // the other side's stored state for this frame: async copy now, consumed after the recursion catches up
+      const float* src = a.stateT + ((size_t)b * p.T + t) * (size_t)(S * kUpad);
+#pragma unroll
+      for (int k = 0; k < (S * kUpad / 4 + kWarp - 1) / kWarp; ++k) {
+        const int cidx = k * kWarp + lane;
+        if (cidx < S * kUpad / 4) fused_cp_async16(stb + 4 * cidx, src + 4 * cidx);
+      }
+      fused_cp_async_commit();
+      if (n + 1 < n_my) {
+        const int tn = t + W * t_step;
+        if (!p.input_logprobas) lse_next = rowlse_b[tn];
+        cst_next = coff_b[tn];
+      }
+    }
+    // ---- prefetch (phase A): the buffer row n-1 used is free as soon as this iteration starts ----
+    if (!PHASE_B && n + SL - 1 < n_my) load_row((rs == 0) ? SL - 1 : rs - 1, t + (SL - 1) * W * t_step);
+    if (tma && lane == 0 && n + SL - 1 + CTCB200_L2_PREFETCH_ROWS < n_my)
+      bulk_prefetch_l2(logits_b + (size_t)(t + (SL - 1 + CTCB200_L2_PREFETCH_ROWS) * W * t_step) * V, row_bytes);
+    TIMED(2, mbar_wait(bars + rs, (par >> rs) & 1u));          // the row has landed
+    par ^= 1u << rs;
+    float* row = rowbuf + (size_t)rs * Vp;
+    float4* row4 = reinterpret_cast<float4*>(row);
+
+    // ---- stage 1: row log-sum-exp (phase A; one pass, the row chunk lives in registers) and the label gather ----
+    if (!PHASE_B && !p.input_logprobas) {
+      float m_run = kNegInf, s_run = 0.0f;
+      if (n4 <= kWarp) {   // narrow rows (V <= 128): one float4 per lane
+        const float4 v = (lane < n4) ? row4[lane] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+        m_run = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        const float mn0 = (m_run == kNegInf || m_run == INFINITY) ? 0.0f : m_run;
+        s_run = hsum4(exp4_shifted(v, mn0));
+      } else
+      for (int base = 0; base < n4; base += 8 * kWarp) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c4 = base + u * kWarp + lane;
+          v[u] = (c4 < n4) ? row4[c4] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+        }
+        float pm[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) pm[u] = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+        const float cm = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
+        const float mn = fmaxf(m_run, cm);
+        const float mn0 = (mn == kNegInf || mn == INFINITY) ? 0.0f : mn;     // tf.reduce_logsumexp convention
+        s_run *= ex2_approx((m_run - mn0) * kLog2e);                         // 0 * 0 when m_run == -inf
+        // (v - max) first, then the scale: a fused v*log2e - max*log2e would lose the exact 0 for |logit| ~ 1e10
+        float ps[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ps[u] = hsum4(exp4_shifted(v[u], mn0));
+        s_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
+        m_run = mn;
+      }
+      const float M = warp_max(m_run);
+      const float M0 = (M == kNegInf || M == INFINITY) ? 0.0f : M;
+      const float mr0 = (m_run == kNegInf || m_run == INFINITY) ? 0.0f : m_run;
+      const float sum = warp_sum(s_run * ex2_approx((mr0 - M0) * kLog2e));
+      lse = M0 + logf(sum);
+      if (lane == 0) a.rowlse[(size_t)b * p.T + t] = lse;
+    }
+    if (!PHASE_B && i >= R) TIMED(4, mbar_wait(sv.empty + slot, use_par ^ 1u));   // slot consumed by the recursion
+    float dd[NS];
+    {
+      float* dst = sv.ringd + slot * kUpad;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int l = lane * NS + j;
+        const bool ok = (l < L) && (tok[j] >= 0) && (tok[j] < V);
+        dd[j] = ok ? row[ok ? tok[j] : 0] - lse : kNegInf;
+        dst[j * kWarp + lane] = dd[j];
+      }
+    }
+    const float h = row[p.blank] - lse;
+    if (lane == 0) sv.ringh[slot] = h;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sv.full_d + slot);
+
+    // ---- stage 1b (phase B): the dense softmax part of the gradient row, in place, while the recursion catches up.
+    // d loss/d logit = d_loss * (softmax * sum_k occ - occ); sum_k occ is 1 for every frame of a feasible sample (it is
+    // the total probability of being somewhere), so the softmax term does not have to wait for the occupancies.
+    if (PHASE_B) {
+      const float2 dl2 = make_float2(dl, dl);
+#pragma unroll 8
+      for (int c4 = lane; c4 < n4; c4 += kWarp) {
+        const float4 e = exp4_shifted(row4[c4], lse);
+        const float2 lo = __fmul2_rn(make_float2(e.x, e.y), dl2), hi = __fmul2_rn(make_float2(e.z, e.w), dl2);
+        row4[c4] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+    }
+
+    // ---- prefetch (phase B): row n+SL-1 goes into the buffer row n-1 used; its TMA store must have drained first,
+    // which is why this sits after the softmax pass rather than at the top of the iteration ----
+    if (PHASE_B && n + SL - 1 < n_my) {
+      if (tma && lane == 0) bulk_store_wait_read();
+      load_row((rs == 0) ? SL - 1 : rs - 1, t + (SL - 1) * W * t_step);
+    }
+
+    // ---- stage 2 (phase B): occupancies of the frame, scattered into the row; then the row leaves by TMA ----
+    if (PHASE_B) {
+      TIMED(5, mbar_wait(sv.full_s + slot, use_par));          // the running side's state for this frame is published
+      TIMED(7, fused_cp_async_wait_all());
+      __syncwarp();
+      const float* ring_state = sv.rings + slot * (S * kUpad);
+      const float K = (float)(lossd_mid + sv.ringc[slot] + cst);   // loss + both renormalisation offsets
+      const float* A = (side == 0) ? ring_state : stb;         // alpha[t]
+      const float* Bn = (side == 0) ? stb : ring_state;        // beta[t+1]
+      float occ[NS], occ_stay[NS], x[NS];
+      float xm = kNegInf;
+      if (!CLASSIC) {
+        float a0[NS], b0[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          a0[j] = A[j * kWarp + lane];
+          b0[j] = Bn[j * kWarp + lane];
+        }
+        float bx = __shfl_down_sync(kFull, b0[0], 1);
+        if (lane == 31) bx = kNegInf;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          x[j] = a0[j] + b0[j];                                 // blank keeps the state: simplified_ctc_loss.py:498-501
+          xm = fmaxf(xm, x[j]);
+          const float bn = (j < NS - 1) ? b0[j + 1] : bx;
+          occ[j] = ex2_approx((K + (a0[j] + dd[j] + bn)) * kLog2e);   // emit label[l]: simplified_ctc_loss.py:503-510
+          const bool ok = (tok[j] != p.blank) && (tok[j] >= 0) && (tok[j] < V);
+          if (!ok) occ[j] = 0.0f;
+        }
+      } else {
+        float a0[NS], a1[NS], b0[NS], b1[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          a0[j] = A[j * kWarp + lane];
+          a1[j] = A[kUpad + j * kWarp + lane];
+          b0[j] = Bn[j * kWarp + lane];
+          b1[j] = Bn[kUpad + j * kWarp + lane];
+        }
+        float bx = __shfl_down_sync(kFull, b1[0], 1);
+        if (lane == 31) bx = kNegInf;
+        float d_left = __shfl_up_sync(kFull, dd[NS - 1], 1);
+        if (lane == 0) d_left = kNegInf;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          const int tp = (j > 0) ? tok[j - 1] : tok_left;
+          const float sj = lse2(a0[j], a1[j]);
+          x[j] = sj + b0[j];                                    // any state -> closed via blank: classic_ctc_loss.py:608-614
+          xm = fmaxf(xm, x[j]);
+          const float bn = (j < NS - 1) ? b1[j + 1] : bx;
+          // diagonal step emitting label[l] (classic_ctc_loss.py:629-639); open -> open is barred on a repeat
+          occ[j] = ex2_approx((K + (dd[j] + ((tok[j] == tp) ? a0[j] : sj) + bn)) * kLog2e);
+          if (!((tok[j] != p.blank) && (tok[j] >= 0) && (tok[j] < V))) occ[j] = 0.0f;
+          // horizontal step re-emitting label[l-1] from the open state (classic_ctc_loss.py:617-626)
+          const float dp = (j > 0) ? dd[j - 1] : d_left;
+          occ_stay[j] = ex2_approx((K + (a1[j] + dp + b1[j])) * kLog2e);
+          if (!((tp != p.blank) && (tp >= 0) && (tp < V))) occ_stay[j] = 0.0f;
+        }
+      }
+      // Scatter the occupancies into the row: row[token] -= d_loss * occ.
+      if (CLASSIC) {   // the horizontal (stay) occupancy of state l+1 re-emits label[l]: same target as state l's move
+        float s_next = __shfl_down_sync(kFull, occ_stay[0], 1);
+        if (lane == 31) s_next = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) occ[j] += (j < NS - 1) ? occ_stay[j + 1] : s_next;
+      }
+      // (shared-memory float atomics: measured faster on B200 than a shuffle-combined or conflict-mask-guarded plain
+      // read-modify-write)
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+        if (occ[j] > 0.0f) atomicAdd(&row[tok[j]], -dl * occ[j]);
+      __syncwarp();
+      const float XM = warp_max(xm);
+      const float XM0 = (XM == kNegInf) ? 0.0f : XM;
+      float xs = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) xs += ex2_approx((x[j] - XM0) * kLog2e);
+      xs = warp_sum(xs);
+      const float occ_blank = (XM == kNegInf) ? 0.0f : __expf(K + (h + (XM + __logf(xs))));
+      if (lane == 0) row[p.blank] -= dl * occ_blank;
+      __syncwarp();
+      float* gdst = a.grad + ((size_t)b * p.T + t) * V;
+      if (tma) {
+        if (lane == 0) {
+          fence_proxy_async();                                  // generic-proxy writes -> visible to the TMA store
+          bulk_store(gdst, row, row_bytes);
+        }
+      } else {
+        for (int k = lane; k < V; k += kWarp) gdst[k] = row[k];
+        __syncwarp();
+      }
+      if (lane == 0) mbar_arrive(sv.empty + slot);              // ring slot and stb are free again
+    }
+    slot += W;
+    if (slot >= R) { slot -= R; use_par ^= 1u; }
+    if (++rs == SL) rs = 0;
+  }
+  if (PHASE_B && tma && lane == 0) bulk_store_wait_read();      // shared memory must outlive the stores reading it
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------------------
+template <int NS, bool CLASSIC, bool TMA>
+__global__ void __launch_bounds__(2 * ((CLASSIC ? 3 : kMaxWorkers) + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
+  const Problem& p = a.p;
+  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL);
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = f.W;
+  const int side = warp / (W + 1), role = warp % (W + 1);      // role 0 = recursion warp, 1..W = row workers
+  const int L = utt_label_len(p, b), n_t = utt_frames(p, b), M = n_t >> 1;
+  const float dl = a.d_loss ? a.d_loss[b] : 1.0f;
+
+  float* xch = reinterpret_cast<float*>(smem + f.off_xch);
+  double* xoff = reinterpret_cast<double*>(smem + f.off_xoff);
+  const SideView sv = side_view(smem, f, side);
+
+  auto reset_sync_state = [&]() {     // one thread: counters to zero, mbarriers to phase 0
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const SideView v = side_view(smem, f, s2);
+      for (int k = 0; k < 3 * f.R; ++k) mbar_init(v.full_d + k, 1u);
+      for (int k = 0; k < W * kMaxRowSlots; ++k) mbar_init(v.bar + k, TMA ? 1u : (unsigned)kWarp);
+    }
+    fence_mbar_init();
+  };
+
+  if (tid == 0) reset_sync_state();
+  __syncthreads();
+
+  // this lane's labels, in registers for the whole kernel
+  int tok[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) tok[j] = utt_token(p, b, lane * NS + j, L);
+  const int tok_left = utt_token(p, b, lane * NS - 1, L);
+
+  long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  (void)tm;
+#ifdef CTCB200_FUSED_TIMING
+  const long long t_start = clock64();
+#endif
+  // recursion state (only meaningful in the two recursion warps)
+  float v0[NS], v1[NS];
+  double c = 0.0;
+  LabelBits<NS> lb;
+  if (CLASSIC) lb = make_label_bits<NS>(p, b, L, lane);
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int l = lane * NS + j;
+    if (side == 0) {            // alpha[0] = log one_hot(state 0, closed)
+      v0[j] = (l == 0) ? 0.0f : kNegInf;
+      v1[j] = kNegInf;
+    } else {                    // beta[n_t] = log one_hot(label_length), both states
+      v0[j] = (l == L) ? 0.0f : kNegInf;
+      v1[j] = v0[j];
+    }
+  }
+
+  // ------------------------------------------------ phase A ------------------------------------------------------------
+  {
+    const int cnt = (side == 0) ? M : n_t - M, tf = (side == 0) ? 0 : n_t - 1, ts = (side == 0) ? 1 : -1;
+    if (role == 0) {
+      if (side == 0) rec_phase<NS, CLASSIC, 0, false>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
+      else rec_phase<NS, CLASSIC, 1, false>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
+    } else {
+      worker_phase<NS, CLASSIC, false, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, tok_left, lane, tm);
+    }
+  }
+
+#ifdef CTCB200_FUSED_TIMING
+  tm[0] = clock64() - t_start;
+  const long long t_mid = clock64();
+#endif
+  // ------------------------------------------------ the middle ---------------------------------------------------------
+  if (role == 0) {
+    float* dst = xch + side * (S * kUpad);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      dst[j * kWarp + lane] = v0[j];
+      if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
+    }
+    if (lane == 0) xoff[side] = c;
+  }
+  __syncthreads();     // also makes phase A's global scratch visible to the whole CTA
+  if (tid == 0) reset_sync_state();
+  LseAcc zacc;
+  for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(xch[q] + xch[S * kUpad + q]);
+  const float lz = zacc.warp_result();
+  const bool dead = (lz == kNegInf);                          // no feasible alignment: loss = +inf, zero gradient
+  const double lossd_mid = -((double)lz + xoff[0] + xoff[1]);  // -log Z
+  __syncthreads();
+
+  // ------------------------------------------------ phase B ------------------------------------------------------------
+  if (!dead) {
+    const int cnt = (side == 0) ? n_t - M : M, tf = (side == 0) ? M : M - 1, ts = (side == 0) ? 1 : -1;
+    if (role == 0) {
+      if (side == 0) rec_phase<NS, CLASSIC, 0, true>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
+      else rec_phase<NS, CLASSIC, 1, true>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
+    } else {
+      worker_phase<NS, CLASSIC, true, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, tok_left, lane, tm);
+    }
+  }
+
+#ifdef CTCB200_FUSED_TIMING
+  tm[1] = clock64() - t_mid;
+  if (a.dbg != nullptr && lane == 0)
+    for (int q = 0; q < 8; ++q) a.dbg[((size_t)b * (2 * (W + 1)) + warp) * 8 + q] = tm[q];
+#endif
+  // ------------------------------------------------ loss and the rows nobody owns --------------------------------------
+  if (side == 0 && role == 0) {
+    // loss = -alpha[T, label_length] (classic_ctc_loss.py:152-165 / simplified_ctc_loss.py:73-83); frames beyond n_t
+    // leave it unchanged.
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+      if (lane * NS + j == L) {
+        const double ld = dead ? (double)INFINITY : -((double)(CLASSIC ? lse2(v0[j], v1[j]) : v0[j]) + c);
+        a.loss[b] = (float)ld;
+      }
+  }
+  if (role > 0) {     // frames beyond logit_length, or every frame of an infeasible sample: exact zeros
+    const int widx = side * W + (role - 1);
+    for (int r = (dead ? 0 : n_t) + widx; r < p.T; r += 2 * W) fused_zero_row(a.grad + ((size_t)b * p.T + r) * p.V, p.V, lane, TMA);
+  }
+}
+
+// ---- host side: one launcher per (variant, row-mover) pair, defined in kf_fused_*.cu --------------------------------
+constexpr int kSmemPerSm = 227 * 1024;
+
+template <bool CLASSIC, bool TMA>
+cudaError_t launch_fused_variant(const FusedArgs& a, cudaStream_t st);
+
+template <int NS, bool CLASSIC, bool TMA>
+static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
+  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL);
+  cudaError_t e = cudaFuncSetAttribute(kf_fused<NS, CLASSIC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, f.total);
+  if (e != cudaSuccess) return e;
+  kf_fused<NS, CLASSIC, TMA><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
+  return cudaGetLastError();
+}
+
+#define CTCB200_DEFINE_FUSED_VARIANT(CLASSIC_, TMA_)                                                        \
+  template <>                                                                                               \
+  cudaError_t launch_fused_variant<CLASSIC_, TMA_>(const FusedArgs& a, cudaStream_t st) {                   \
+    switch (a.p.NS) {                                                                                       \
+      case 1: return launch_fused_ns<1, CLASSIC_, TMA_>(a, st);                                             \
+      case 2: return launch_fused_ns<2, CLASSIC_, TMA_>(a, st);                                             \
+      case 3: return launch_fused_ns<3, CLASSIC_, TMA_>(a, st);                                             \
+      case 4: return launch_fused_ns<4, CLASSIC_, TMA_>(a, st);                                             \
+      case 5: return launch_fused_ns<5, CLASSIC_, TMA_>(a, st);                                             \
+      case 6: return launch_fused_ns<6, CLASSIC_, TMA_>(a, st);                                             \
+      case 7: return launch_fused_ns<7, CLASSIC_, TMA_>(a, st);                                             \
+      case 8: return launch_fused_ns<8, CLASSIC_, TMA_>(a, st);                                             \
+      case 9: return launch_fused_ns<9, CLASSIC_, TMA_>(a, st);                                             \
+      case 10: return launch_fused_ns<10, CLASSIC_, TMA_>(a, st);                                           \
+      case 11: return launch_fused_ns<11, CLASSIC_, TMA_>(a, st);                                           \
+      case 12: return launch_fused_ns<12, CLASSIC_, TMA_>(a, st);                                           \
+      case 13: return launch_fused_ns<13, CLASSIC_, TMA_>(a, st);                                           \
+      case 14: return launch_fused_ns<14, CLASSIC_, TMA_>(a, st);                                           \
+      case 15: return launch_fused_ns<15, CLASSIC_, TMA_>(a, st);                                           \
+      case 16: return launch_fused_ns<16, CLASSIC_, TMA_>(a, st);                                           \
+      default: return cudaErrorInvalidValue;                                                                \
+    }                                                                                                       \
+  }
+
+}  // namespace ctcb200

@@ -1,0 +1,6 @@
+// Instantiations of the fused kernel: classic variant, rows moved by 1-D TMA.
+#include "kf_fused.cuh"
+
+namespace ctcb200 {
+CTCB200_DEFINE_FUSED_VARIANT(true, true)
+}  // namespace ctcb200
