@@ -42,6 +42,9 @@ extern "C" {
 #define CTCB200_FORCE_STAGED 2u    /* ctcb200_loss_grad: use the three staged kernels (K1 softmax+gather, K2 recursion,
                                       K3 gradient) even where the fused single-launch kernel applies */
 
+#define CTCB200_FORCE_FUSED 4u     /* ctcb200_loss_grad: use the fused kernel even for narrow vocabularies (V < 64), where the
+                                      staged kernels are the default */
+
 /* Profiling aid: flags bits 8..15 select which stages of ctcb200_loss_grad are enqueued (bit 8+i = i-th name of
  * ctcb200_stage_names()); 0 = all.  A partial call must follow a full call on the same workspace and inputs. */
 #define CTCB200_STAGE_SHIFT 8

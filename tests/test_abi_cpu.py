@@ -33,12 +33,12 @@ def test_error_strings_and_descriptor_validation():
     assert lib.ctcb200_strerror(0) == b"ok"
     for code in range(-6, 0):
         assert lib.ctcb200_strerror(code) not in (b"ok", b"unknown error")
-    good = _lib.Desc(4, 10, 8, 3, 0, _lib.CLASSIC, 4, 0)
+    good = _lib.Desc(4, 10, 64, 3, 0, _lib.CLASSIC, 4, 0)
     assert lib.ctcb200_workspace_bytes(ctypes.byref(good), _lib.WS_LOSS_GRAD) > 0
     assert lib.ctcb200_workspace_bytes(ctypes.byref(good), _lib.WS_HESSIAN) > lib.ctcb200_workspace_bytes(
         ctypes.byref(good), _lib.WS_LOSS_GRAD)
     for bad in (_lib.Desc(-1, 10, 8, 3, 0, 0, 4, 0),      # negative batch
-                _lib.Desc(4, 10, 8, 3, 8, 0, 4, 0),       # blank out of range
+                _lib.Desc(4, 10, 8, 3, 8, 0, 4, 0),       # blank out of range (V = 8)
                 _lib.Desc(4, 10, 8, 3, 0, 2, 4, 0),       # unknown variant
                 _lib.Desc(4, 10, 8, 3, 0, 0, 4, 1 << 20),  # unknown flag
                 _lib.Desc(4, 1000, 8, 600, 0, 0, 601, 0),  # more than 512 label states
@@ -59,6 +59,10 @@ def test_error_strings_and_descriptor_validation():
     staged = _lib.Desc(4, 10, 29, 3, 0, _lib.CLASSIC, 4, _lib.FORCE_STAGED)
     assert lib.ctcb200_stage_names(ctypes.byref(staged)) == b"k1_softmax_gather,k2_recursion,k3_grad"
     assert lib.ctcb200_launches_per_call(ctypes.byref(good)) == 1 and lib.ctcb200_launches_per_call(ctypes.byref(staged)) == 3
+    narrow = _lib.Desc(4, 10, 29, 3, 0, _lib.CLASSIC, 4, 0)        # character-sized vocabulary: staged unless forced
+    assert lib.ctcb200_launches_per_call(ctypes.byref(narrow)) == 3
+    narrow.flags = _lib.FORCE_FUSED
+    assert lib.ctcb200_stage_names(ctypes.byref(narrow)) == b"kf_fused"
 
 
 def test_python_face_has_no_cpu_fallback():

@@ -31,12 +31,12 @@ def _pkg():
 
 @pytest.fixture(params=["fused", "staged"])
 def kernel_path(request):
-    """The loss+gradient call has two device paths: the fused single-launch kernel (taken whenever V % 4 == 0 and the
-    shared-memory plan fits) and the three staged kernels K1/K2/K3 (every other shape, and the states / Hessian
-    entry points).  Both must agree with the oracle on every shape."""
+    """The loss+gradient call has two device paths: the fused single-launch kernel (default for V >= 64 when its
+    shared-memory plan fits) and the three staged kernels K1/K2/K3 (narrow vocabularies, oversized rows, and the
+    states / Hessian entry points).  Both are forced in turn and must agree with the oracle on every shape."""
     from tf_seq2seq_losses_b200 import _lib
     old = _lib.DEFAULT_FLAGS
-    _lib.DEFAULT_FLAGS = _lib.FORCE_STAGED if request.param == "staged" else 0
+    _lib.DEFAULT_FLAGS = _lib.FORCE_STAGED if request.param == "staged" else _lib.FORCE_FUSED
     yield request.param
     _lib.DEFAULT_FLAGS = old
 

@@ -15,6 +15,7 @@ CLASSIC = 0
 SIMPLIFIED = 1
 INPUT_LOGPROBAS = 1
 FORCE_STAGED = 2
+FORCE_FUSED = 4
 WS_LOSS_GRAD, WS_STATES, WS_HESSIAN = 0, 1, 2
 MAX_STATES = 512
 MAX_TOKENS = 32768

@@ -34,7 +34,7 @@
 
 namespace ctcb200 {
 
-constexpr int kMaxRowSlots = 3;     // TMA row buffers per worker: current + prefetch (+ one draining its TMA store)
+constexpr int kMaxRowSlots = 4;     // row buffers per worker: current + prefetch(es); phase A may own one more (see XA)
 constexpr int kFusedGroup = 4;      // frames per unrolled group (renormalisation cadence, see recursion.cuh)
 #ifndef CTCB200_L2_PREFETCH_ROWS
 #define CTCB200_L2_PREFETCH_ROWS 0  // rows (per worker) requested into L2 ahead of the shared-memory load; measured on B200: 2/4/8 rows make the kernel 6/20/33% slower, so it is off
@@ -150,19 +150,26 @@ __device__ __forceinline__ float hsum4(float4 e) {
 
 // ---- shared-memory layout (one definition for host sizing and device carving) ---------------------------------------
 struct FusedLayout {
-  int W, R, SL;             // workers per side, ring depth (= 2W, a multiple of W), row buffers per worker
+  int W, R, SL, XA;         // workers per side, ring depth (= 2W), row buffers per worker, extra phase-A row buffers (0/1)
   int off_xch, off_xoff, off_side0, total;
   // offsets inside a side block
-  int s_ctl, s_bar, s_row, s_ringd, s_ringh, s_rings, s_ringc, s_stbuf, side_bytes;
+  int s_ctl, s_bar, s_row, s_aux, s_ringd, s_ringh, side_bytes;
+  // offsets inside the aux block (phase B view)
+  int x_rings, x_ringc, x_stbuf;
 };
 
 __host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL) {
+// Phase A is latency-bound by the bytes it keeps in flight, phase B needs the state ring and the stored-state staging
+// buffers instead: the `aux` block is the union of the two (XA extra row buffers per side in phase A; rings / ringc /
+// stbuf in phase B), which is what lets 4 workers x 3 row buffers fit next to a second CTA on the SM.
+__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL, int XA) {
   FusedLayout f;
   f.W = W;
   f.R = 2 * W;
   f.SL = SL;
+  f.XA = XA;
+  const int Vp = (V + 3) & ~3;
   int o = 0;
   f.off_xch = o;  o += 2 * S * Upad * 4;
   f.off_xoff = o; o += 2 * 8;
@@ -171,13 +178,16 @@ __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int 
   f.s_ctl = s;   s += 3 * f.R * 8;                            // ring barriers: full_d[R], full_s[R], empty[R]
   f.s_bar = s;   s += W * kMaxRowSlots * 8;
   s = fl_align(s, 128);
-  f.s_row = s;   s += W * SL * ((V + 3) & ~3) * 4;
+  f.s_row = s;   s += W * SL * Vp * 4;
+  int x = 0;
+  f.x_rings = x; x += f.R * S * Upad * 4;
+  f.x_ringc = x; x += f.R * 8;
+  x = fl_align(x, 16);
+  f.x_stbuf = x; x += W * S * Upad * 4;
+  const int xa_bytes = XA * W * Vp * 4;
+  f.s_aux = s;   s += fl_align(x > xa_bytes ? x : xa_bytes, 16);
   f.s_ringd = s; s += f.R * Upad * 4;
   f.s_ringh = s; s += fl_align(f.R * 4, 16);
-  f.s_rings = s; s += f.R * S * Upad * 4;
-  f.s_ringc = s; s += f.R * 8;
-  s = fl_align(s, 16);
-  f.s_stbuf = s; s += W * S * Upad * 4;
   f.side_bytes = fl_align(s, 128);
   f.off_side0 = o;
   f.total = o + 2 * f.side_bytes;
@@ -192,7 +202,7 @@ struct FusedArgs {
   const float* d_loss;  // [B] or null
   float* loss;          // [B]
   float* grad;          // [B,T,V]
-  int W, SL;
+  int W, SL, XA;
   int tma;              // 1: rows move by 1-D TMA (V % 4 == 0, 16-byte aligned bases); 0: by 4-byte cp.async / plain stores
   long long* dbg;       // [B][warps][8] when built with CTCB200_FUSED_TIMING, else unused
 };
@@ -206,7 +216,8 @@ struct SideView {
   unsigned long long* empty;    // [R] slot released: by the recursion once it has read the inputs (phase A), by the
                                 //     worker once the frame's gradient row is finished (phase B)
   unsigned long long* bar;   // [W][kMaxRowSlots]
-  float* row;         // [W][SL][V]
+  float* row;         // [W][SL][Vp]
+  float* aux_rows;    // [W][Vp]  phase A only: one extra row buffer per worker (aliases rings / ringc / stbuf)
   float* ringd;       // [R][Upad]
   float* ringh;       // [R]
   float* rings;       // [R][S*Upad]
@@ -223,11 +234,12 @@ __device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLa
   v.empty = ctl + 2 * f.R;
   v.bar = reinterpret_cast<unsigned long long*>(base + f.s_bar);
   v.row = reinterpret_cast<float*>(base + f.s_row);
+  v.aux_rows = reinterpret_cast<float*>(base + f.s_aux);
   v.ringd = reinterpret_cast<float*>(base + f.s_ringd);
   v.ringh = reinterpret_cast<float*>(base + f.s_ringh);
-  v.rings = reinterpret_cast<float*>(base + f.s_rings);
-  v.ringc = reinterpret_cast<double*>(base + f.s_ringc);
-  v.stbuf = reinterpret_cast<float*>(base + f.s_stbuf);
+  v.rings = reinterpret_cast<float*>(base + f.s_aux + f.x_rings);
+  v.ringc = reinterpret_cast<double*>(base + f.s_aux + f.x_ringc);
+  v.stbuf = reinterpret_cast<float*>(base + f.s_aux + f.x_stbuf);
   return v;
 }
 
@@ -318,16 +330,19 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   constexpr float kLog2e = 1.4426950408889634f;
   const Problem& p = a.p;
-  const int W = f.W, R = f.R, SL = f.SL, V = p.V, Vp = (V + 3) & ~3, n4 = Vp >> 2;
+  const int W = f.W, R = f.R, V = p.V, Vp = (V + 3) & ~3, n4 = Vp >> 2;
+  const int SL = PHASE_B ? f.SL : f.SL + f.XA;      // phase A may own one more row buffer (see fused_layout)
   const int n_my = (count > w) ? (count - w + W - 1) / W : 0;
   const unsigned row_bytes = (unsigned)V * 4u;
   constexpr bool tma = TMA;
   const float* logits_b = p.logits + (size_t)b * p.T * V;
-  float* rowbuf = sv.row + (size_t)w * SL * Vp;
+  float* rowbuf = sv.row + (size_t)w * f.SL * Vp;
+  float* rowx = sv.aux_rows + (size_t)w * Vp;
+  auto slot_ptr = [&](int q) { return (q < f.SL) ? rowbuf + (size_t)q * Vp : rowx; };
   // Brings logits row `t` into row buffer q; completion is signalled on bars[q] either by the TMA transaction count
   // (one elected lane) or, when rows are not 16-byte aligned, by every lane's cp.async completion.
   auto load_row = [&](int q, int t) {
-    float* dst = rowbuf + (size_t)q * Vp;
+    float* dst = slot_ptr(q);
     const float* src = logits_b + (size_t)t * V;
     if (tma) {
       if (lane == 0) {
@@ -351,7 +366,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       bulk_prefetch_l2(logits_b + (size_t)(t_first + (w + q * W) * t_step) * V, row_bytes);
   if (!tma)   // pad lanes of the (4-float aligned) row buffers never receive data: make them neutral once
     for (int q = 0; q < SL; ++q)
-      for (int k = V + lane; k < Vp; k += kWarp) rowbuf[(size_t)q * Vp + k] = kNegInf;
+      for (int k = V + lane; k < Vp; k += kWarp) slot_ptr(q)[k] = kNegInf;
   for (int q = 0; q < SL - 1 && q < n_my; ++q) load_row(q, t_first + (w + q * W) * t_step);
   int slot = w % R;        // ring slot of frame i = w + n*W
   unsigned use_par = 0;    // (i / R) & 1
@@ -391,10 +406,13 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       bulk_prefetch_l2(logits_b + (size_t)(t + (SL - 1 + CTCB200_L2_PREFETCH_ROWS) * W * t_step) * V, row_bytes);
     TIMED(2, mbar_wait(bars + rs, (par >> rs) & 1u));          // the row has landed
     par ^= 1u << rs;
-    float* row = rowbuf + (size_t)rs * Vp;
+    float* row = slot_ptr(rs);
     float4* row4 = reinterpret_cast<float4*>(row);
 
     // ---- stage 1: row log-sum-exp (phase A; one pass, the row chunk lives in registers) and the label gather ----
+#ifdef CTCB200_FUSED_TIMING
+    const long long t_s0 = clock64();
+#endif
     if (!PHASE_B && !p.input_logprobas) {
       float m_run = kNegInf, s_run = 0.0f;
       if (n4 <= kWarp) {   // narrow rows (V <= 128): one float4 per lane
@@ -431,6 +449,10 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       lse = M0 + logf(sum);
       if (lane == 0) a.rowlse[(size_t)b * p.T + t] = lse;
     }
+#ifdef CTCB200_FUSED_TIMING
+    tm[6] += clock64() - t_s0;   // workers: row statistics
+    const long long t_g0 = clock64();
+#endif
     if (!PHASE_B && i >= R) TIMED(4, mbar_wait(sv.empty + slot, use_par ^ 1u));   // slot consumed by the recursion
     float dd[NS];
     {
@@ -447,6 +469,9 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     if (lane == 0) sv.ringh[slot] = h;
     __syncwarp();
     if (lane == 0) mbar_arrive(sv.full_d + slot);
+#ifdef CTCB200_FUSED_TIMING
+    tm[3] += clock64() - t_g0;   // workers: ring wait + gather + publish
+#endif
 
     // ---- stage 1b (phase B): the dense softmax part of the gradient row, in place, while the recursion catches up.
     // d loss/d logit = d_loss * (softmax * sum_k occ - occ); sum_k occ is 1 for every frame of a feasible sample (it is
@@ -573,7 +598,7 @@ __global__ void __launch_bounds__(2 * ((CLASSIC ? 3 : kMaxWorkers) + 1) * kWarp,
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const Problem& p = a.p;
-  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL);
+  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = f.W;
   const int side = warp / (W + 1), role = warp % (W + 1);      // role 0 = recursion warp, 1..W = row workers
@@ -699,7 +724,7 @@ cudaError_t launch_fused_variant(const FusedArgs& a, cudaStream_t st);
 
 template <int NS, bool CLASSIC, bool TMA>
 static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
-  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL);
+  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA);
   cudaError_t e = cudaFuncSetAttribute(kf_fused<NS, CLASSIC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, f.total);
   if (e != cudaSuccess) return e;
   kf_fused<NS, CLASSIC, TMA><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);

@@ -39,7 +39,7 @@ off = a256(rows * 4) * 2 + a256(rows * Upad * 4) + a256(srows * 4)       # byte 
 W = int(os.environ.get("CTCB200_FUSED_W", "4" if variant == _lib.SIMPLIFIED else "3"))
 warps = 2 * (W + 1)
 dbg = ws[off: off + B * warps * 8 * 8].view(torch.int64).reshape(B, warps, 8).cpu().numpy().astype(np.float64)
-names = ["phaseA", "phaseB", "tma_wait", "dcount_wait", "ccount_wait", "scount_wait", "done_wait", "state_cpasync_wait"]
+names = ["phaseA", "phaseB", "tma_wait", "rec:d_wait|work:gather", "ccount_wait", "scount_wait", "rec:done_wait|work:stats", "state_cpasync_wait"]
 for wi in range(warps):
     side, role = divmod(wi, W + 1)
     m = dbg[:, wi].mean(axis=0)
