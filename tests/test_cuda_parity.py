@@ -257,9 +257,13 @@ def test_degenerate_shapes(variant, kernel_path):
     assert list(x.grad.shape) == [0, 4, 3]
 
 
+@pytest.mark.parametrize("k4", ["registers", "generic"])
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
-def test_hessian_matches_oracle(variant):
-    """ClassicCtcLossData.hessian / SimplifiedCtcLossData.hessian vs the oracle (literal for tiny, matrix-free for cfg-4 shape)."""
+def test_hessian_matches_oracle(variant, k4, monkeypatch):
+    """ClassicCtcLossData.hessian / SimplifiedCtcLossData.hessian vs the oracle (literal for tiny, matrix-free for cfg-4 shape).
+    The Hessian kernel has a register-resident form (U <= 128) and a generic shared-memory form; both are checked."""
+    if k4 == "generic":
+        monkeypatch.setenv("CTCB200_K4_GENERIC", "1")
     for (B, T, V, L, seed) in [(2, 4, 3, 2, 0), (2, 6, 5, 3, 1), (3, 50, 32, 15, 2)]:
         logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
         if T == 6:

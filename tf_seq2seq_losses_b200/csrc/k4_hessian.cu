@@ -10,8 +10,11 @@
 //     H[t,k,t',k'] = -exp(loss + J_sym) + g[t,k] g[t',k']          (t' != t)
 //     H[t,k,t ,k'] = [k == k'] g[t,k]   + g[t,k] g[t ,k']          (g = -occupancy, base_loss.py:200-237)
 // and zero for infeasible samples and frames beyond logit_length (base_loss.py:240-258).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "occupancy.cuh"
+#include "recursion.cuh"
 
 namespace ctcb200 {
 
@@ -247,6 +250,277 @@ __global__ void __launch_bounds__(kK4Warps * kWarp)
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Register-resident variant for U <= 128 (NS <= 4), which covers every shape for which the O(T^2 V^2) output is
+// affordable.  Same algorithm; the chain state lives in registers (recursion.cuh steps, neighbour by shuffle), the
+// occupancies of a frame are computed from registers and subtracted from a shared-memory row that was pre-loaded with
+// g[t,k] * g[t',:], and the finished row is written (or contracted with d_gradient) at once.  ~5x fewer instructions
+// per (t, k, t') than the generic kernel above.
+template <int NS, bool CLASSIC>
+struct ChainRegs {
+  float v0[NS], v1[NS];
+};
+
+// occupancies of one frame given alpha-side state (a0,a1) and beta-side state (b0,b1); subtracts them from row[]
+template <int NS, bool CLASSIC>
+__device__ __forceinline__ void subtract_frame_occupancies(const float* a0, const float* a1, const float* b0,
+                                                           const float* b1, const float* dd, float h, float K,
+                                                           const int* tok, int tok_left, int blank, int V, int lane,
+                                                           float* row) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  float occ[NS], occ_stay[NS], x[NS];
+  float xm = kNegInf;
+  if (!CLASSIC) {
+    float bx = __shfl_down_sync(kFull, b0[0], 1);
+    if (lane == 31) bx = kNegInf;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      x[j] = a0[j] + b0[j];
+      xm = fmaxf(xm, x[j]);
+      const float bn = (j < NS - 1) ? b0[j + 1] : bx;
+      occ[j] = ex2_approx((K + (a0[j] + dd[j] + bn)) * kLog2e);
+      if (!((tok[j] != blank) && (tok[j] >= 0) && (tok[j] < V))) occ[j] = 0.0f;
+    }
+  } else {
+    float bx = __shfl_down_sync(kFull, b1[0], 1);
+    if (lane == 31) bx = kNegInf;
+    float d_left = __shfl_up_sync(kFull, dd[NS - 1], 1);
+    if (lane == 0) d_left = kNegInf;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const int tp = (j > 0) ? tok[j - 1] : tok_left;
+      const float sj = lse2(a0[j], a1[j]);
+      x[j] = sj + b0[j];
+      xm = fmaxf(xm, x[j]);
+      const float bn = (j < NS - 1) ? b1[j + 1] : bx;
+      occ[j] = ex2_approx((K + (dd[j] + ((tok[j] == tp) ? a0[j] : sj) + bn)) * kLog2e);
+      if (!((tok[j] != blank) && (tok[j] >= 0) && (tok[j] < V))) occ[j] = 0.0f;
+      const float dp = (j > 0) ? dd[j - 1] : d_left;
+      occ_stay[j] = ex2_approx((K + (a1[j] + dp + b1[j])) * kLog2e);
+      if (!((tp != blank) && (tp >= 0) && (tp < V))) occ_stay[j] = 0.0f;
+    }
+    float s_next = __shfl_down_sync(kFull, occ_stay[0], 1);
+    if (lane == 31) s_next = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) occ[j] += (j < NS - 1) ? occ_stay[j + 1] : s_next;
+  }
+#pragma unroll
+  for (int j = 0; j < NS; ++j)
+    if (occ[j] > 0.0f) atomicAdd(&row[tok[j]], -occ[j]);
+  const float XM = warp_max(xm);
+  const float XM0 = (XM == kNegInf) ? 0.0f : XM;
+  float xs = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) xs += ex2_approx((x[j] - XM0) * kLog2e);
+  xs = warp_sum(xs);
+  const float occ_blank = (XM == kNegInf) ? 0.0f : __expf(K + (h + (XM + __logf(xs))));
+  if (lane == 0) atomicAdd(&row[blank], -occ_blank);
+}
+
+template <int NS>
+__device__ __forceinline__ void load_state(const float* src, int planes, int lane, float* v0, float* v1) {
+  constexpr int kUpad = NS * kWarp;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    v0[j] = src[j * kWarp + lane];
+    v1[j] = (planes == 2) ? src[kUpad + j * kWarp + lane] : kNegInf;
+  }
+}
+
+template <int NS, bool CLASSIC, bool HVP>
+__global__ void __launch_bounds__(kK4Warps * kWarp)
+    k4_hessian_regs(Problem p, Scratch s, const float* __restrict__ g, float* __restrict__ hessian,
+                    const float* __restrict__ d_gradient, float* __restrict__ hvp_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
+  const int b = blockIdx.x / p.T, t = blockIdx.x % p.T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = utt_label_len(p, b), n_t = utt_frames(p, b);
+  const double lossd = s.lossd[b];
+  const bool dead = (lossd == (double)INFINITY) || (t >= n_t);
+  const size_t TV = (size_t)p.T * p.V;
+  float* slab = HVP ? nullptr : hessian + ((size_t)b * p.T + t) * p.V * TV;
+  float* out_hv = HVP ? hvp_out + ((size_t)b * p.T + t) * p.V : nullptr;
+  if (dead) {
+    if (HVP) for (int k = tid; k < p.V; k += blockDim.x) out_hv[k] = 0.0f;
+    else for (size_t i = tid; i < (size_t)p.V * TV; i += blockDim.x) slab[i] = 0.0f;
+    return;
+  }
+  float* row = reinterpret_cast<float*>(smem_raw) + (size_t)warp * p.V;
+  int tok[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) tok[j] = utt_token(p, b, lane * NS + j, L);
+  const int tok_left = utt_token(p, b, lane * NS - 1, L);
+  LabelBits<NS> lb;
+  if (CLASSIC) lb = make_label_bits<NS>(p, b, L, lane);
+
+  const size_t row_pitch = (size_t)S * kUpad;
+  const float* alpha_b = s.alphaT + (size_t)b * (p.T + 1) * row_pitch;
+  const float* beta_b = s.betaT + (size_t)b * (p.T + 1) * row_pitch;
+  const float* d_b = s.dT + (size_t)b * p.T * kUpad;
+  const float* h_b = s.h + (size_t)b * p.T;
+  const float* g_b = g + (size_t)b * TV;
+  const float* dg_b = HVP ? d_gradient + (size_t)b * TV : nullptr;
+  const double* ca_b = s.ca + (size_t)b * (p.T + 1);
+  const double* cb_b = s.cb + (size_t)b * (p.T + 1);
+
+  // frame t's own inputs, reused by every token's two chains
+  float a0t[NS], a1t[NS], b0t[NS], b1t[NS], dt[NS];
+  load_state<NS>(alpha_b + (size_t)t * row_pitch, S, lane, a0t, a1t);
+  load_state<NS>(beta_b + (size_t)(t + 1) * row_pitch, S, lane, b0t, b1t);
+#pragma unroll
+  for (int j = 0; j < NS; ++j) dt[j] = d_b[(size_t)t * kUpad + j * kWarp + lane];
+  const float ht = h_b[t];
+
+  // emits one finished row: dense store or contraction with d_gradient
+  auto finish_row = [&](int t2, float& hv, float* hk) {
+    __syncwarp();
+    if (HVP) {
+      const float* dg2 = dg_b + (size_t)t2 * p.V;
+      for (int k2 = lane; k2 < p.V; k2 += kWarp) hv += row[k2] * dg2[k2];
+    } else {
+      float* dst = hk + (size_t)t2 * p.V;
+      for (int k2 = lane; k2 < p.V; k2 += kWarp) dst[k2] = row[k2];
+    }
+    __syncwarp();
+  };
+
+  for (int k = warp; k < p.V; k += kK4Warps) {
+    float* hk = HVP ? nullptr : slab + (size_t)k * TV;
+    // is k the blank or one of this utterance's label tokens?
+    bool mine = false;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) mine |= (lane * NS + j < L) && (tok[j] == k);
+    const bool in_label = (k == p.blank) || __any_sync(kFull, mine);
+    if (!in_label) {             // g[t,k] == 0 and every path term vanishes
+      if (HVP) { if (lane == 0) out_hv[k] = 0.0f; }
+      else for (size_t i = lane; i < TV; i += kWarp) hk[i] = 0.0f;
+      continue;
+    }
+    const float gk = g_b[(size_t)t * p.V + k];
+    float hv = 0.0f;
+    if (!HVP) for (size_t i = (size_t)n_t * p.V + lane; i < TV; i += kWarp) hk[i] = 0.0f;   // frames beyond logit_length
+    // same frame: [k == k'] g[t,k] + g[t,k] g[t,k']
+    {
+      const float* g2 = g_b + (size_t)t * p.V;
+      for (int k2 = lane; k2 < p.V; k2 += kWarp) row[k2] = gk * g2[k2] + ((k2 == k) ? gk : 0.0f);
+      finish_row(t, hv, hk);
+    }
+    // ---- later frames: push alpha[t] through "emit k", propagate forward ----
+    float v0[NS], v1[NS];
+    {
+      float a_left0 = __shfl_up_sync(kFull, a0t[NS - 1], 1), a_left1 = __shfl_up_sync(kFull, a1t[NS - 1], 1);
+      float d_left = __shfl_up_sync(kFull, dt[NS - 1], 1);
+      if (lane == 0) { a_left0 = kNegInf; a_left1 = kNegInf; d_left = kNegInf; }
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int tp = (j > 0) ? tok[j - 1] : tok_left;             // label[l-1]
+        const float pa0 = (j > 0) ? a0t[j - 1] : a_left0, pa1 = (j > 0) ? a1t[j - 1] : a_left1;
+        const float pd = (j > 0) ? dt[j - 1] : d_left;
+        if (k == p.blank) {
+          v0[j] = ht + (CLASSIC ? lse2(a0t[j], a1t[j]) : a0t[j]);
+          v1[j] = kNegInf;
+        } else if (!CLASSIC) {
+          v0[j] = (tp == k) ? pa0 + pd : kNegInf;
+          v1[j] = kNegInf;
+        } else {
+          const bool rep_prev = (j > 0) ? ((lb.rep >> (j - 1)) & 1u) : lb.rep_left;
+          const float xprev = rep_prev ? pa0 : lse2(pa0, pa1);
+          v0[j] = kNegInf;
+          v1[j] = (tp == k) ? lse2(a1t[j] + pd, pd + xprev) : kNegInf;
+        }
+      }
+    }
+    for (int t2 = t + 1; t2 < n_t; ++t2) {
+      float bn0[NS], bn1[NS], d2[NS];
+      load_state<NS>(beta_b + (size_t)(t2 + 1) * row_pitch, S, lane, bn0, bn1);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) d2[j] = d_b[(size_t)t2 * kUpad + j * kWarp + lane];
+      const float h2 = h_b[t2];
+      const float* g2 = g_b + (size_t)t2 * p.V;
+      for (int k2 = lane; k2 < p.V; k2 += kWarp) row[k2] = gk * g2[k2];
+      __syncwarp();
+      const float K = (float)(lossd + ca_b[t] + cb_b[t2 + 1]);
+      subtract_frame_occupancies<NS, CLASSIC>(v0, v1, bn0, bn1, d2, h2, K, tok, tok_left, p.blank, p.V, lane, row);
+      finish_row(t2, hv, hk);
+      if (CLASSIC) alpha_step_classic<NS>(v0, v1, d2, h2, lane, lb);
+      else alpha_step_simplified<NS>(v0, d2, h2, lane);
+    }
+    // ---- earlier frames: pull beta[t+1] back through "emit k", propagate backward ----
+    {
+      float b_right1 = __shfl_down_sync(kFull, CLASSIC ? b1t[0] : b0t[0], 1);
+      if (lane == 31) b_right1 = kNegInf;
+      float d_left = __shfl_up_sync(kFull, dt[NS - 1], 1);
+      if (lane == 0) d_left = kNegInf;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int l = lane * NS + j;
+        const int tp = (j > 0) ? tok[j - 1] : tok_left;
+        const float bnext = (j < NS - 1) ? (CLASSIC ? b1t[j + 1] : b0t[j + 1]) : b_right1;   // beta[t+1, l+1(,open)]
+        if (k == p.blank) {
+          v0[j] = ht + b0t[j];
+          v1[j] = v0[j];
+        } else {
+          const float mv = (l < L && tok[j] == k) ? dt[j] + bnext : kNegInf;
+          v0[j] = mv;
+          if (CLASSIC) {
+            const float pd = (j > 0) ? dt[j - 1] : d_left;
+            const float sv = (l >= 1 && tp == k) ? pd + b1t[j] : kNegInf;
+            const bool rep = (lb.rep >> j) & 1u;
+            v1[j] = lse2(sv, rep ? kNegInf : mv);
+          } else {
+            v1[j] = kNegInf;
+          }
+        }
+      }
+    }
+    for (int t2 = t - 1; t2 >= 0; --t2) {
+      float al0[NS], al1[NS], d2[NS];
+      load_state<NS>(alpha_b + (size_t)t2 * row_pitch, S, lane, al0, al1);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) d2[j] = d_b[(size_t)t2 * kUpad + j * kWarp + lane];
+      const float h2 = h_b[t2];
+      const float* g2 = g_b + (size_t)t2 * p.V;
+      for (int k2 = lane; k2 < p.V; k2 += kWarp) row[k2] = gk * g2[k2];
+      __syncwarp();
+      const float K = (float)(lossd + ca_b[t2] + cb_b[t + 1]);
+      subtract_frame_occupancies<NS, CLASSIC>(al0, al1, v0, v1, d2, h2, K, tok, tok_left, p.blank, p.V, lane, row);
+      finish_row(t2, hv, hk);
+      if (CLASSIC) beta_step_classic<NS>(v0, v1, d2, h2, lane, lb);
+      else beta_step_simplified<NS>(v0, d2, h2, lane);
+    }
+    if (HVP) {
+      hv = warp_sum(hv);
+      if (lane == 0) out_hv[k] = hv;
+    }
+  }
+}
+
+template <int NS, bool CLASSIC, bool HVP>
+static cudaError_t launch_k4_regs(const Problem& p, const Scratch& s, const float* g, float* hessian,
+                                  const float* d_gradient, float* hvp_out, cudaStream_t st) {
+  const size_t smem = (size_t)kK4Warps * p.V * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k4_hessian_regs<NS, CLASSIC, HVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const unsigned grid = (unsigned)((long long)p.B * p.T);
+  k4_hessian_regs<NS, CLASSIC, HVP><<<grid, kK4Warps * kWarp, smem, st>>>(p, s, g, hessian, d_gradient, hvp_out);
+  return cudaGetLastError();
+}
+
+template <bool CLASSIC, bool HVP>
+static cudaError_t launch_k4_regs_ns(const Problem& p, const Scratch& s, const float* g, float* hessian,
+                                     const float* d_gradient, float* hvp_out, cudaStream_t st) {
+  switch (p.NS) {
+    case 1: return launch_k4_regs<1, CLASSIC, HVP>(p, s, g, hessian, d_gradient, hvp_out, st);
+    case 2: return launch_k4_regs<2, CLASSIC, HVP>(p, s, g, hessian, d_gradient, hvp_out, st);
+    case 3: return launch_k4_regs<3, CLASSIC, HVP>(p, s, g, hessian, d_gradient, hvp_out, st);
+    case 4: return launch_k4_regs<4, CLASSIC, HVP>(p, s, g, hessian, d_gradient, hvp_out, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 static size_t hessian_smem_bytes(const Problem& p) {
   const int Vpad = (p.V + 7) & ~7;
   const int per_warp = (p.Upad + kWarp) + 2 * p.S * p.Upad;
@@ -271,12 +545,18 @@ cudaError_t launch_hessian(const Problem& p, const Scratch& s, const float* g, f
                            const float* d_gradient, float* hvp_out, cudaStream_t st) {
   if (p.B == 0 || p.T == 0) return cudaSuccess;
   const bool classic = p.variant == CTCB200_CLASSIC;
+  const bool regs = (p.NS <= 4) && ((size_t)kK4Warps * p.V * sizeof(float) <= 200 * 1024) && getenv("CTCB200_K4_GENERIC") == nullptr;
   if (hessian != nullptr) {
-    cudaError_t e = classic ? launch_k4<true, false>(p, s, g, hessian, nullptr, nullptr, st)
-                            : launch_k4<false, false>(p, s, g, hessian, nullptr, nullptr, st);
+    cudaError_t e;
+    if (regs) e = classic ? launch_k4_regs_ns<true, false>(p, s, g, hessian, nullptr, nullptr, st)
+                          : launch_k4_regs_ns<false, false>(p, s, g, hessian, nullptr, nullptr, st);
+    else e = classic ? launch_k4<true, false>(p, s, g, hessian, nullptr, nullptr, st)
+                     : launch_k4<false, false>(p, s, g, hessian, nullptr, nullptr, st);
     if (e != cudaSuccess) return e;
   }
   if (hvp_out != nullptr) {
+    if (regs) return classic ? launch_k4_regs_ns<true, true>(p, s, g, nullptr, d_gradient, hvp_out, st)
+                             : launch_k4_regs_ns<false, true>(p, s, g, nullptr, d_gradient, hvp_out, st);
     return classic ? launch_k4<true, true>(p, s, g, nullptr, d_gradient, hvp_out, st)
                    : launch_k4<false, true>(p, s, g, nullptr, d_gradient, hvp_out, st);
   }
