@@ -422,3 +422,56 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     torch.cuda.synchronize()
     assert torch.equal(loss_h, loss_d.cpu()) and torch.equal(grad_h, grad_d.cpu())
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# randomized shape sweep: every frame count / label length / worker configuration corner of the fused kernel
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_random_shape_sweep(variant, kernel_path):
+    """Small random problems with frame counts 0..9 around the meet-in-the-middle split, empty labels, infeasible
+    samples, V not a multiple of 4, non-zero blank -- compared with the C restatement (pinned against the numpy oracle)."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(1234 + variant)
+    for trial in range(24):
+        B = int(rng.integers(1, 6))
+        T = int(rng.integers(1, 14))
+        V = int(rng.choice([3, 4, 7, 8, 33, 64, 100, 260]))
+        Lw = int(rng.integers(1, 8))
+        blank = int(rng.integers(0, V))
+        logits = (rng.standard_normal((B, T, V)) * rng.choice([0.1, 1.0, 5.0])).astype(np.float32)
+        labels = rng.integers(0, V - 1, size=(B, Lw)).astype(np.int32)
+        labels = np.where(labels >= blank, labels + 1, labels).astype(np.int32)
+        ll = rng.integers(0, Lw + 1, size=B).astype(np.int32)
+        tl = rng.integers(0, T + 1, size=B).astype(np.int32)
+        want_loss, want_grad = c_oracle.loss_grad(labels, logits, ll, tl, blank, variant)
+        x = _cuda(logits).requires_grad_(True)
+        loss = _fn(variant)(_cuda(labels), x, _cuda(ll), _cuda(tl), blank)
+        torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)).sum().backward()
+        _loss_close(loss.detach().cpu().numpy(), want_loss)
+        got = x.grad.cpu().numpy()
+        assert not np.isnan(got).any()
+        assert np.max(np.abs(got - want_grad)) <= GRAD_ATOL_SHORT, (trial, B, T, V, Lw, blank, ll, tl)
+
+
+@pytest.mark.parametrize("cfg", [(1, 2, 0), (2, 2, 0), (2, 3, 0), (3, 2, 1), (3, 3, 0), (4, 2, 0), (4, 2, 1)],
+                         ids=lambda c: "W%d_SL%d_XA%d" % c)
+def test_fused_worker_configurations(cfg, monkeypatch):
+    """Every (workers per side, row buffers, extra phase-A buffer) plan of the fused kernel gives the same answer."""
+    from tf_seq2seq_losses_b200 import _lib
+    monkeypatch.setenv("CTCB200_FUSED_W", str(cfg[0]))
+    monkeypatch.setenv("CTCB200_FUSED_SL", str(cfg[1]))
+    monkeypatch.setenv("CTCB200_FUSED_XA", str(cfg[2]))
+    old = _lib.DEFAULT_FLAGS
+    _lib.DEFAULT_FLAGS = _lib.FORCE_FUSED
+    try:
+        for (B, T, V, L, seed) in [(5, 61, 96, 20, 0), (3, 30, 37, 9, 1)]:
+            logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
+            want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, SIMPLIFIED)
+            x = _cuda(logits).requires_grad_(True)
+            loss = _pkg().simple_ctc_loss(_cuda(labels), x, _cuda(ll), _cuda(tl), 0)
+            loss.sum().backward()
+            _loss_close(loss.detach().cpu().numpy(), want_loss)
+            assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= GRAD_ATOL_SHORT
+    finally:
+        _lib.DEFAULT_FLAGS = old
