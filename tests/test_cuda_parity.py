@@ -475,3 +475,33 @@ def test_fused_worker_configurations(cfg, monkeypatch):
             assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= GRAD_ATOL_SHORT
     finally:
         _lib.DEFAULT_FLAGS = old
+
+
+def test_size_limits_both_paths():
+    """The largest supported label-state count (U = 512 -> 16 states per lane) on both device paths, and a vocabulary
+    whose rows do not fit the fused kernel's shared-memory plan (V = 32768 -> staged kernels by construction)."""
+    from oracle import c_oracle
+    from tf_seq2seq_losses_b200 import _lib
+    B, T, V, L = 2, 560, 64, 511
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=17, ragged=False)
+    ll[1], tl[1] = 300, 420
+    want_loss, want_grad = c_oracle.loss_grad(labels, logits, ll, tl, 0, CLASSIC)
+    old = _lib.DEFAULT_FLAGS
+    try:
+        for flags in (_lib.FORCE_FUSED, _lib.FORCE_STAGED):
+            _lib.DEFAULT_FLAGS = flags
+            x = _cuda(logits).requires_grad_(True)
+            loss = _pkg().classic_ctc_loss(_cuda(labels), x, _cuda(ll), _cuda(tl), 0)
+            loss.sum().backward()
+            _loss_close(loss.detach().cpu().numpy(), want_loss)
+            assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= GRAD_ATOL_LONG
+    finally:
+        _lib.DEFAULT_FLAGS = old
+    B, T, V, L = 2, 40, 32768, 10
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=18)
+    want_loss, want_grad = c_oracle.loss_grad(labels, logits, ll, tl, 0, SIMPLIFIED)
+    x = _cuda(logits).requires_grad_(True)
+    loss = _pkg().simple_ctc_loss(_cuda(labels), x, _cuda(ll), _cuda(tl), 0)
+    loss.sum().backward()
+    _loss_close(loss.detach().cpu().numpy(), want_loss)
+    assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= GRAD_ATOL_SHORT
