@@ -36,9 +36,6 @@ namespace ctcb200 {
 
 constexpr int kMaxRowSlots = 4;     // row buffers per worker: current + prefetch(es); phase A may own one more (see XA)
 constexpr int kFusedGroup = 4;      // frames per unrolled group (renormalisation cadence, see recursion.cuh)
-#ifndef CTCB200_L2_PREFETCH_ROWS
-#define CTCB200_L2_PREFETCH_ROWS 0  // rows (per worker) requested into L2 ahead of the shared-memory load; measured on B200: 2/4/8 rows make the kernel 6/20/33% slower, so it is off
-#endif
 constexpr int kMaxWorkers = 4;
 
 // ---- PTX helpers -----------------------------------------------------------------------------------------------
@@ -72,29 +69,6 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsi
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-// TMA prefetch of a global range into L2: deepens the HBM pipeline without spending shared memory on more row buffers
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ void spin_until(const unsigned* p, unsigned need) {
-  if (ld_acquire(p) >= need) return;
-#ifndef CTCB200_SPIN_MAXNS
-#define CTCB200_SPIN_MAXNS 20
-#endif
-  unsigned ns = 20;       // back-off: a waiting warp must not eat the issue slots of the warps it waits for
-  do {
-    __nanosleep(ns);
-    if (ns < CTCB200_SPIN_MAXNS) ns <<= 1;
-  } while (ld_acquire(p) < need);
 }
 // 1-D TMA store: shared -> global bulk copy tracked by the per-thread bulk async-group
 __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
@@ -360,10 +334,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   const float* rowlse_b = a.rowlse + (size_t)b * p.T;
   const double* coff_b = a.coff + (size_t)b * p.T;
 
-  // prologue: the first SL-1 rows are in flight before any is consumed, the next few are on their way into L2
-  if (tma && lane == 0)
-    for (int q = SL - 1; q < SL - 1 + CTCB200_L2_PREFETCH_ROWS && q < n_my; ++q)
-      bulk_prefetch_l2(logits_b + (size_t)(t_first + (w + q * W) * t_step) * V, row_bytes);
+  // prologue: the first SL-1 rows are in flight before any is consumed
   if (!tma)   // pad lanes of the (4-float aligned) row buffers never receive data: make them neutral once
     for (int q = 0; q < SL; ++q)
       for (int k = V + lane; k < Vp; k += kWarp) slot_ptr(q)[k] = kNegInf;
@@ -402,8 +373,6 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     }
     // ---- prefetch (phase A): the buffer row n-1 used is free as soon as this iteration starts ----
     if (!PHASE_B && n + SL - 1 < n_my) load_row((rs == 0) ? SL - 1 : rs - 1, t + (SL - 1) * W * t_step);
-    if (tma && lane == 0 && n + SL - 1 + CTCB200_L2_PREFETCH_ROWS < n_my)
-      bulk_prefetch_l2(logits_b + (size_t)(t + (SL - 1 + CTCB200_L2_PREFETCH_ROWS) * W * t_step) * V, row_bytes);
     TIMED(2, mbar_wait(bars + rs, (par >> rs) & 1u));          // the row has landed
     par ^= 1u << rs;
     float* row = slot_ptr(rs);
