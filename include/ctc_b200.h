@@ -111,6 +111,15 @@ int ctcb200_states(const ctcb200_desc* desc, const float* logits, const int32_t*
                    float* loss, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * gamma: log-probability of reaching state (t2, l2[, s2]) from state (t1, l1[, s1]); -inf for t2 < t1.  Replaces
+ * ClassicCtcLossData.gamma (classic_ctc_loss.py:167-308, float32 [B,T+1,U,2,T+1,U,2]) and SimplifiedCtcLossData.gamma
+ * (simplified_ctc_loss.py:85-191, float32 [B,T+1,U,T+1,U]).  desc->U must be the true max(label_length)+1 and at most
+ * 128 (the tensor is O(T^2 U^2)); workspace sized with CTCB200_WS_STATES.
+ */
+int ctcb200_gamma(const ctcb200_desc* desc, const float* logits, const int32_t* labels, const int32_t* label_length,
+                  const int32_t* logit_length, float* gamma, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Dense Hessian of the per-sample loss w.r.t. the log-probabilities, [B,T,V,T,V].  Replaces
  * BaseCtcLossData.hessian (base_loss.py:186-260) without materialising gamma (classic_ctc_loss.py:167-308,
  * simplified_ctc_loss.py:85-191).  Also returns loss [B] and gradient [B,T,V] (either may be NULL).

@@ -283,6 +283,29 @@ def test_hessian_matches_oracle(variant, k4, monkeypatch):
 
 
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_gamma_matches_oracle(variant):
+    """ClassicCtcLossData.gamma / SimplifiedCtcLossData.gamma vs the literal oracle unfolding; gamma[:,0,0(,0)] == alpha
+    (tests/test_hessian.py:62-87); -inf below the time diagonal, identity on it (classic_ctc_loss.py:204-213,286-308)."""
+    for (B, T, V, L, seed) in [(2, 4, 3, 2, 0), (2, 6, 5, 3, 1), (3, 12, 7, 8, 2), (2, 40, 9, 36, 3)]:
+        logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
+        if T == 6:
+            labels[0, :2] = 2           # repeated token
+        data, _ = orc.ctc_loss_data(labels, logits, ll, tl, 0, variant)
+        want = data.gamma
+        obj, _ = _data_obj((logits, labels, ll, tl), variant)
+        got = obj.gamma.cpu().numpy()
+        assert got.shape == want.shape
+        assert np.array_equal(np.isneginf(got), np.isneginf(want))
+        fin = np.isfinite(want)
+        assert np.max(np.abs(got[fin] - want[fin])) <= 1e-4
+        first = got[:, 0, 0, 0] if variant == CLASSIC else got[:, 0, 0]
+        alpha = obj.alpha.cpu().numpy()
+        fin = np.isfinite(alpha)
+        assert np.array_equal(np.isneginf(first), np.isneginf(alpha))
+        assert np.max(np.abs(first[fin] - alpha[fin])) <= 1e-4
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
 def test_second_derivative_through_logproba_chain(variant):
     """ctc_loss_from_logproba differentiated twice (tests/test_hessian.py:110-147, test_classic_ctc_loss.py:443-477)."""
     pkg = _pkg()

@@ -26,7 +26,7 @@ _LIB_PATH = os.environ.get("CTCB200_LIB", os.path.join(os.path.dirname(os.path.a
 EXPORTED_SYMBOLS = (
     "ctcb200_version", "ctcb200_strerror", "ctcb200_stage_names", "ctcb200_launches_per_call",
     "ctcb200_workspace_bytes", "ctcb200_loss_grad", "ctcb200_states",
-    "ctcb200_hessian", "ctcb200_hvp", "ctcb200_host_create", "ctcb200_host_loss_grad",
+    "ctcb200_hessian", "ctcb200_hvp", "ctcb200_gamma", "ctcb200_host_create", "ctcb200_host_loss_grad",
     "ctcb200_host_grad_device_ptr", "ctcb200_host_destroy",
 )
 
@@ -72,6 +72,8 @@ def load() -> ctypes.CDLL:
     lib.ctcb200_states.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, fp, vp, ctypes.c_size_t, vp]
     lib.ctcb200_hessian.restype = ctypes.c_int
     lib.ctcb200_hessian.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, fp, vp, ctypes.c_size_t, vp]
+    lib.ctcb200_gamma.restype = ctypes.c_int
+    lib.ctcb200_gamma.argtypes = [dp, fp, i32p, i32p, i32p, fp, vp, ctypes.c_size_t, vp]
     lib.ctcb200_hvp.restype = ctypes.c_int
     lib.ctcb200_hvp.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, vp, ctypes.c_size_t, vp]
     lib.ctcb200_host_create.restype = ctypes.c_int
@@ -155,6 +157,21 @@ def states(desc: Desc, logits, labels, label_length, logit_length):
                                     _ptr(logit_length), _ptr(alpha), _ptr(beta), _ptr(loss), _ptr(ws), ws.numel(),
                                     _stream(dev)))
     return alpha, beta, loss
+
+
+def gamma(desc: Desc, logits, labels, label_length, logit_length):
+    """ctcb200_gamma.  Returns gamma in the reference layout ([B,T+1,U,2,T+1,U,2] classic, [B,T+1,U,T+1,U] simplified)."""
+    _require_cuda(logits, "logits")
+    dev = logits.device
+    B, T, U = desc.B, desc.T, desc.U
+    shape = (B, T + 1, U, 2, T + 1, U, 2) if desc.variant == CLASSIC else (B, T + 1, U, T + 1, U)
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    ws = _workspace(desc, WS_STATES, dev)
+    if B > 0:
+        with torch.cuda.device(dev):
+            check(load().ctcb200_gamma(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
+                                       _ptr(logit_length), _ptr(out), _ptr(ws), ws.numel(), _stream(dev)))
+    return out
 
 
 def hessian(desc: Desc, logits, labels, label_length, logit_length):

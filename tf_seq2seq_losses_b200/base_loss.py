@@ -181,11 +181,12 @@ class BaseCtcLossData:
     def beta(self) -> torch.Tensor:
         return self._states[1]
 
-    @property
+    @cached_property
     def gamma(self) -> torch.Tensor:
-        # classic_ctc_loss.py:167-308 / simplified_ctc_loss.py:85-191.  The O(T^2 U^2) tensor is only an
-        # intermediate of the reference's Hessian; the device Hessian kernel never forms it.
-        raise NotImplementedError("gamma is not materialised by the B200 path; use .hessian / hessian_vector_product")
+        """Transition log-probabilities between any two states, [B,T+1,U,2,T+1,U,2] classic / [B,T+1,U,T+1,U] simplified
+        (classic_ctc_loss.py:167-308 / simplified_ctc_loss.py:85-191).  O(T^2 U^2): small shapes only (U <= 128).  The
+        Hessian kernels do not use it; it completes the data-class surface."""
+        return _lib.gamma(self._desc, *self._args())
 
 
 def ctc_loss_from_logproba(labels, logprobas, label_length, logit_length, blank_index, ctc_loss_data_cls,

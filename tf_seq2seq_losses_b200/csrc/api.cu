@@ -175,6 +175,22 @@ int ctcb200_states(const ctcb200_desc* desc, const float* logits, const int32_t*
   return CTCB200_OK;
 }
 
+int ctcb200_gamma(const ctcb200_desc* desc, const float* logits, const int32_t* labels, const int32_t* label_length,
+                  const int32_t* logit_length, float* gamma, void* workspace, size_t workspace_bytes, void* stream) {
+  Problem p; Scratch s;
+  int rc = check_common(desc, &p, CTCB200_WS_STATES, logits, labels, label_length, logit_length, workspace,
+                        workspace_bytes, &s, nullptr);
+  if (rc != CTCB200_OK) return rc;
+  if (desc->U <= 0) return CTCB200_ERR_BAD_DESCRIPTOR;   // the output shape depends on the true U
+  if (p.NS > 4) return CTCB200_ERR_UNSUPPORTED_SIZE;
+  if (p.B == 0) return CTCB200_OK;
+  if (gamma == nullptr) return CTCB200_ERR_NULL_POINTER;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CTCB200_CUDA(launch_softmax_gather(p, s, st));
+  CTCB200_CUDA(launch_gamma(p, s, gamma, st));
+  return CTCB200_OK;
+}
+
 int ctcb200_hessian(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
                     const int32_t* label_length, const int32_t* logit_length, float* hessian, float* loss,
                     float* grad_logprobas, void* workspace, size_t workspace_bytes, void* stream) {

@@ -129,6 +129,7 @@ int fused_pick_workers(const Problem& p);
 cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss, float* loss, float* grad, int W,
                          cudaStream_t st);
 cudaError_t launch_export_states(const Problem& p, const Scratch& s, float* alpha, float* beta, cudaStream_t st);
+cudaError_t launch_gamma(const Problem& p, const Scratch& s, float* gamma, cudaStream_t st);
 cudaError_t launch_hessian(const Problem& p, const Scratch& s, const float* g, float* hessian,
                            const float* d_gradient, float* hvp_out, cudaStream_t st);
 

@@ -12,7 +12,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tf_seq2seq_losses_b200 import _lib  # noqa: E402
 
-B, T, V, L = 256, 1000, 1024, 200
+B, T, V, L = int(os.environ.get("CTCB200_TIMING_B", "256")), 1000, 1024, 200
 variant = _lib.CLASSIC if (len(sys.argv) > 1 and sys.argv[1] == "classic") else _lib.SIMPLIFIED
 g = torch.Generator().manual_seed(0)
 logits = torch.randn((B, T, V), generator=g).cuda()
