@@ -38,8 +38,9 @@ rows, srows = B * T, B * (T + 1) * S * Upad
 off = a256(rows * 4) * 2 + a256(rows * Upad * 4) + a256(srows * 4)       # byte offset of the beta scratch
 W = int(os.environ.get("CTCB200_FUSED_W", "4" if variant == _lib.SIMPLIFIED else "3"))
 warps = 2 * (W + 1)
-dbg = ws[off: off + B * warps * 8 * 8].view(torch.int64).reshape(B, warps, 8).cpu().numpy().astype(np.float64)
-names = ["phaseA", "phaseB", "tma_wait", "rec:d_wait|work:gather", "ccount_wait", "scount_wait", "rec:done_wait|work:stats", "state_cpasync_wait"]
+dbg = ws[off: off + B * warps * 12 * 8].view(torch.int64).reshape(B, warps, 12).cpu().numpy().astype(np.float64)
+names = ["phaseA", "phaseB", "tma_wait", "rec:d_wait|work:gather", "ccount_wait", "scount_wait", "rec:done_wait|work:stats", "state_cpasync_wait",
+         "B:softmax", "B:occupancy", "B:scatter", "B:blank+store"]
 for wi in range(warps):
     side, role = divmod(wi, W + 1)
     m = dbg[:, wi].mean(axis=0)
