@@ -27,6 +27,9 @@ WORKLOADS = {
     "cfg1": (32, 500, 29, 100, "classic"),
     "cfg2": (256, 1000, 1024, 200, "simplified"),
     "cfg4": (256, 1600, 5000, 400, "classic"),
+    # BASELINE.json configs[4] at its full batch on one GPU: 65.5 GB logits + 65.5 GB gradient + 11 GB workspace; inputs are
+    # generated on the device (no host copy exists, so this workload has no e2e / CPU leg)
+    "cfg4full": (2048, 1600, 5000, 400, "classic"),
 }
 METRIC = "CTC loss+grad samples/s at B=256 T=1000 V=1024 L=200"
 
@@ -193,11 +196,25 @@ def main():
     else:
         b0, b1 = shard_bounds(B, world, rank)      # the named batch is cut into contiguous slices
         local_B, global_B = b1 - b0, B
-    logits_h, labels_h, ll_h, tl_h = synth(local_B, T, V, L, 1000 + rank, args.ragged)
-    logits, labels, ll, tl = logits_h.to(dev), labels_h.to(dev), ll_h.to(dev), tl_h.to(dev)
+    on_device = local_B * T * V * 4 > 16e9           # too large for a host copy: generate on the device
+    if on_device:
+        args.no_e2e = args.no_cpu_baseline = True
+        gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+        logits = torch.empty((local_B, T, V), dtype=torch.float32, device=dev)
+        for b0 in range(0, local_B, 64):
+            logits[b0:b0 + 64].normal_(generator=gen)
+        labels = torch.randint(1, V, (local_B, L), generator=gen, dtype=torch.int32, device=dev)
+        tl = torch.full((local_B,), T, dtype=torch.int32, device=dev)
+        ll = torch.full((local_B,), L, dtype=torch.int32, device=dev)
+        if args.ragged:
+            tl = torch.randint(T // 2, T + 1, (local_B,), generator=gen, dtype=torch.int32, device=dev)
+            ll = torch.randint(L // 2, L + 1, (local_B,), generator=gen, dtype=torch.int32, device=dev)
+    else:
+        logits_h, labels_h, ll_h, tl_h = synth(local_B, T, V, L, 1000 + rank, args.ragged)
+        logits, labels, ll, tl = logits_h.to(dev), labels_h.to(dev), ll_h.to(dev), tl_h.to(dev)
     desc = _lib.make_desc(logits, labels, 0, vid, L + 1, _lib.FORCE_STAGED if args.staged else 0)
     lib = _lib.load()
-    ws = torch.empty(max(lib.ctcb200_workspace_bytes(ctypes.byref(desc), _lib.WS_LOSS_GRAD), 256), dtype=torch.uint8, device=dev)
+    ws = torch.empty(max(lib.ctcb200_workspace_bytes(ctypes.byref(desc), _lib.WS_LOSS_GRAD_LOGITS), 256), dtype=torch.uint8, device=dev)
     loss = torch.empty((local_B,), dtype=torch.float32, device=dev)
     grad = torch.empty_like(logits)
     stream = torch.cuda.current_stream(dev)

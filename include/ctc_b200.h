@@ -63,6 +63,10 @@ extern "C" {
 #define CTCB200_WS_LOSS_GRAD 0
 #define CTCB200_WS_STATES 1
 #define CTCB200_WS_HESSIAN 2
+/* ctcb200_loss_grad called with grad_logits != NULL and grad_logprobas == NULL (the training call): when the fused kernel
+ * serves the shape this is about a third of CTCB200_WS_LOSS_GRAD (no gathered rows, one state tensor instead of two);
+ * otherwise the two are equal.  A workspace sized with CTCB200_WS_LOSS_GRAD is always accepted as well. */
+#define CTCB200_WS_LOSS_GRAD_LOGITS 3
 
 typedef struct ctcb200_desc {
   int32_t B;       /* batch size                      (>= 0) */

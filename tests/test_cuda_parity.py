@@ -413,6 +413,67 @@ def test_config4_large_vocab_slice(kernel_path):
         assert np.array_equal(grad[b], np.zeros_like(grad[b]))
 
 
+def test_config4_full_batch_on_one_gpu():
+    """BASELINE.json configs[4] at its full size on ONE GPU: classic_ctc_loss B=2048 T=1600 V=5000 L=400 (65.5 GB of
+    logits + 65.5 GB of gradient + 11 GB of workspace), logits generated on the device, with the edge samples of
+    SURVEY.md 8(d) injected.  Checked through size-independent properties over the whole batch and against the oracle
+    on a subsample."""
+    import ctypes
+    from tf_seq2seq_losses_b200 import _lib
+    B, T, V, L = 2048, 1600, 5000, 400
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150e9:
+        pytest.skip(f"needs 150 GB of free device memory, have {free / 1e9:.0f} GB")
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(11)
+    logits = torch.empty((B, T, V), dtype=torch.float32, device=dev)
+    for b0 in range(0, B, 64):                       # generate in slices: randn's temporaries stay small
+        logits[b0:b0 + 64].normal_(generator=gen)
+    labels = torch.randint(1, V, (B, L), generator=gen, dtype=torch.int32, device=dev)
+    tl = torch.full((B,), T, dtype=torch.int32, device=dev)
+    ll = torch.full((B,), L, dtype=torch.int32, device=dev)
+    tl[8:] = torch.randint(T // 2, T + 1, (B - 8,), generator=gen, dtype=torch.int32, device=dev)
+    ll[8:] = torch.randint(L // 2, L + 1, (B - 8,), generator=gen, dtype=torch.int32, device=dev)
+    logits[0, :, 1:] = -float("inf")                 # only the blank is possible: infeasible, +inf and zero gradient
+    tt = torch.arange(T, device=dev)                 # sample 1: 1e10 on one valid alignment (3 frames per label, then a blank)
+    logits[1, tt, torch.where(tt % 4 == 3, torch.zeros_like(tt), labels[1, tt // 4].long())] = 1e10
+    ll[2], tl[2] = 400, 300                          # more labels than frames: +inf
+    ll[3] = 0                                        # empty label: loss = -sum_t h[t]
+    tl[4] = 0                                        # no frames: +inf (label_length > 0)
+    desc = _lib.make_desc(logits, labels, 0, _lib.CLASSIC, L + 1, 0)
+    lib = _lib.load()
+    assert lib.ctcb200_stage_names(ctypes.byref(desc)).decode() == "kf_fused"
+    n = lib.ctcb200_workspace_bytes(ctypes.byref(desc), _lib.WS_LOSS_GRAD_LOGITS)
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    loss = torch.empty(B, device=dev)
+    grad = torch.empty_like(logits)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.ctcb200_loss_grad(ctypes.byref(desc), P(logits), P(labels), P(ll), P(tl), None, P(loss), P(grad), None,
+                                     P(ws), n, st))
+    torch.cuda.synchronize()
+    got_loss = loss.cpu().numpy()
+    assert np.isinf(got_loss[[0, 2, 4]]).all() and np.isfinite(np.delete(got_loss, [0, 2, 4])).all()
+    want_inf_rows = torch.tensor([0, 2, 4], device=dev)
+    assert float(grad[want_inf_rows].abs().max()) == 0.0
+    # whole-batch properties, in slices to bound temporaries: rows sum to zero, padded rows are exactly zero, no NaN
+    for b0 in range(0, B, 128):
+        g = grad[b0:b0 + 128]
+        assert not torch.isnan(g).any()
+        assert float(g.sum(dim=2).abs().max()) < 5e-3
+        mask = torch.arange(T, device=dev)[None, :] >= tl[b0:b0 + 128, None]
+        assert float(g[mask].abs().max() if mask.any() else 0.0) == 0.0
+    # sample 1: the 1e10 path has probability one -> loss 0 and a zero gradient
+    assert abs(float(got_loss[1])) < 1e-3 and float(grad[1].abs().max()) < 1e-6
+    idx = [3, 5, 1024, 2047]
+    want_loss, want_grad, _ = orc.loss_and_grad_logits(labels[idx].cpu().numpy(), logits[idx].cpu().numpy(),
+                                                        ll[idx].cpu().numpy(), tl[idx].cpu().numpy(), 0, CLASSIC)
+    _loss_close(got_loss[idx], want_loss)
+    err = float(np.max(np.abs(grad[idx].cpu().numpy() - want_grad)))
+    print(f"[config4 full batch] grad max-abs err {err:.3e}")
+    assert err <= GRAD_ATOL_LONG
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # boundary behaviour
 # ------------------------------------------------------------------------------------------------------------------

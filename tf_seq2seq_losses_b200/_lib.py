@@ -16,7 +16,7 @@ SIMPLIFIED = 1
 INPUT_LOGPROBAS = 1
 FORCE_STAGED = 2
 FORCE_FUSED = 4
-WS_LOSS_GRAD, WS_STATES, WS_HESSIAN = 0, 1, 2
+WS_LOSS_GRAD, WS_STATES, WS_HESSIAN, WS_LOSS_GRAD_LOGITS = 0, 1, 2, 3
 MAX_STATES = 512
 MAX_TOKENS = 32768
 
@@ -135,7 +135,7 @@ def loss_grad(desc: Desc, logits, labels, label_length, logit_length, d_loss=Non
     if want_grad_logits:
         gl = grad_logits_out if grad_logits_out is not None else torch.empty_like(logits)
     gp = torch.empty_like(logits) if want_grad_logprobas else None
-    ws = _workspace(desc, WS_LOSS_GRAD, dev)
+    ws = _workspace(desc, WS_LOSS_GRAD_LOGITS if (want_grad_logits and not want_grad_logprobas) else WS_LOSS_GRAD, dev)
     with torch.cuda.device(dev):
         check(load().ctcb200_loss_grad(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
                                        _ptr(logit_length), _ptr(d_loss), _ptr(loss), _ptr(gl), _ptr(gp),

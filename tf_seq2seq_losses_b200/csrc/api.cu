@@ -31,12 +31,20 @@ struct Carve {
   size_t take(size_t bytes) { size_t o = off; off += align256(bytes); return o; }
 };
 
-static size_t carve(const Problem& p, int what, char* base, Scratch* s, float** grad_tmp) {
+// `fused_only`: the call is served by the fused kernel alone, which needs the row log-sum-exps, ONE state tensor and one
+// offset vector; the gathered rows, the second state tensor and its offsets (staged kernels) are left out.
+static size_t carve(const Problem& p, int what, bool fused_only, char* base, Scratch* s, float** grad_tmp) {
   Carve c;
+#ifdef CTCB200_FUSED_TIMING
+  const bool staged = true;            // the instrumented kernel writes its counters into the (otherwise unused) beta scratch
+  (void)fused_only;
+#else
+  const bool staged = !fused_only;
+#endif
   const size_t rows = (size_t)p.B * p.T, srows = (size_t)p.B * (p.T + 1) * p.S * p.Upad;
-  const size_t o_lse = c.take(rows * 4), o_h = c.take(rows * 4), o_d = c.take(rows * p.Upad * 4);
-  const size_t o_a = c.take(srows * 4), o_b = c.take(srows * 4), o_loss = c.take((size_t)p.B * 4);
-  const size_t o_ca = c.take((size_t)p.B * (p.T + 1) * 8), o_cb = c.take((size_t)p.B * (p.T + 1) * 8);
+  const size_t o_lse = c.take(rows * 4), o_h = c.take(staged ? rows * 4 : 0), o_d = c.take(staged ? rows * p.Upad * 4 : 0);
+  const size_t o_a = c.take(srows * 4), o_b = c.take(staged ? srows * 4 : 0), o_loss = c.take((size_t)p.B * 4);
+  const size_t o_ca = c.take((size_t)p.B * (p.T + 1) * 8), o_cb = c.take(staged ? (size_t)p.B * (p.T + 1) * 8 : 0);
   const size_t o_ld = c.take((size_t)p.B * 8);
   size_t o_g = 0;
   if (what == CTCB200_WS_HESSIAN) o_g = c.take(rows * p.V * 4);
@@ -55,6 +63,22 @@ static size_t carve(const Problem& p, int what, char* base, Scratch* s, float** 
   return c.off;
 }
 
+// The fused kernel takes the loss+gradient call whenever its shared-memory plan fits (rows move by TMA when V % 4 == 0
+// and the bases are 16-byte aligned, by 4-byte cp.async otherwise).
+static int fused_workers(const ctcb200_desc* desc, const Problem& p) {
+  if (desc->flags & CTCB200_FORCE_STAGED) return 0;
+  // Narrow vocabularies (character models, V < 64) are latency-bound on the T-step chain rather than on row traffic;
+  // there the staged recursion kernel, which streams the compact gathered rows, is measured faster (B=32 T=500 V=29:
+  // 191 us staged vs 239 us fused) unless the caller insists.
+  if (p.V < 64 && !(desc->flags & CTCB200_FORCE_FUSED)) return 0;
+  return fused_pick_workers(p);
+}
+
+// WS_LOSS_GRAD_LOGITS shrinks to the fused kernel's needs whenever that kernel will take the call
+static bool fused_only_ws(const ctcb200_desc* desc, const Problem& p, int what) {
+  return what == CTCB200_WS_LOSS_GRAD_LOGITS && p.T > 0 && fused_workers(desc, p) > 0;
+}
+
 static int check_common(const ctcb200_desc* desc, Problem* p, int what, const float* logits, const int32_t* labels,
                         const int32_t* label_length, const int32_t* logit_length, void* ws, size_t ws_bytes,
                         Scratch* s, float** grad_tmp) {
@@ -65,13 +89,14 @@ static int check_common(const ctcb200_desc* desc, Problem* p, int what, const fl
     if (p->T > 0 && logits == nullptr) return CTCB200_ERR_NULL_POINTER;
     if (p->Lw > 0 && labels == nullptr) return CTCB200_ERR_NULL_POINTER;
   }
-  const size_t need = carve(*p, what, nullptr, nullptr, nullptr);
+  const bool fo = fused_only_ws(desc, *p, what);
+  const size_t need = carve(*p, what, fo, nullptr, nullptr, nullptr);
   if (need > 0 && p->B > 0) {
     if (ws == nullptr) return CTCB200_ERR_NULL_POINTER;
     if (reinterpret_cast<uintptr_t>(ws) & 255) return CTCB200_ERR_MISALIGNED;
     if (ws_bytes < need) return CTCB200_ERR_WORKSPACE_TOO_SMALL;
   }
-  carve(*p, what, static_cast<char*>(ws), s, grad_tmp);
+  carve(*p, what, fo, static_cast<char*>(ws), s, grad_tmp);
   p->logits = logits; p->labels = labels; p->label_length = label_length; p->logit_length = logit_length;
   return CTCB200_OK;
 }
@@ -105,17 +130,6 @@ const char* ctcb200_strerror(int code) {
   }
 }
 
-// The fused kernel takes the loss+gradient call whenever its shared-memory plan fits (rows move by TMA when V % 4 == 0
-// and the bases are 16-byte aligned, by 4-byte cp.async otherwise).
-static int fused_workers(const ctcb200_desc* desc, const Problem& p) {
-  if (desc->flags & CTCB200_FORCE_STAGED) return 0;
-  // Narrow vocabularies (character models, V < 64) are latency-bound on the T-step chain rather than on row traffic;
-  // there the staged recursion kernel, which streams the compact gathered rows, is measured faster (B=32 T=500 V=29:
-  // 191 us staged vs 239 us fused) unless the caller insists.
-  if (p.V < 64 && !(desc->flags & CTCB200_FORCE_FUSED)) return 0;
-  return fused_pick_workers(p);
-}
-
 const char* ctcb200_stage_names(const ctcb200_desc* desc) {
   Problem p;
   if (make_problem(desc, &p) == CTCB200_OK && fused_workers(desc, p) > 0) return "kf_fused";
@@ -132,8 +146,8 @@ int ctcb200_launches_per_call(const ctcb200_desc* desc) {
 size_t ctcb200_workspace_bytes(const ctcb200_desc* desc, int what) {
   Problem p;
   if (make_problem(desc, &p) != CTCB200_OK) return 0;
-  if (what < CTCB200_WS_LOSS_GRAD || what > CTCB200_WS_HESSIAN) return 0;
-  return carve(p, what, nullptr, nullptr, nullptr);
+  if (what < CTCB200_WS_LOSS_GRAD || what > CTCB200_WS_LOSS_GRAD_LOGITS) return 0;
+  return carve(p, what, fused_only_ws(desc, p, what), nullptr, nullptr, nullptr);
 }
 
 int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
@@ -141,14 +155,16 @@ int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32
                       float* grad_logits, float* grad_logprobas, void* workspace, size_t workspace_bytes,
                       void* stream) {
   Problem p; Scratch s;
-  int rc = check_common(desc, &p, CTCB200_WS_LOSS_GRAD, logits, labels, label_length, logit_length, workspace,
-                        workspace_bytes, &s, nullptr);
+  // loss + d/dlogits alone is the fused kernel's call (when its plan fits) and then needs the smaller workspace only
+  const bool logits_only = grad_logits != nullptr && grad_logprobas == nullptr;
+  int rc = check_common(desc, &p, logits_only ? CTCB200_WS_LOSS_GRAD_LOGITS : CTCB200_WS_LOSS_GRAD, logits, labels,
+                        label_length, logit_length, workspace, workspace_bytes, &s, nullptr);
   if (rc != CTCB200_OK) return rc;
   if (p.B == 0) return CTCB200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* loss_out = loss ? loss : s.loss;
   const int W = fused_workers(desc, p);
-  if (W > 0 && grad_logits != nullptr && grad_logprobas == nullptr && p.T > 0) {
+  if (W > 0 && logits_only && p.T > 0) {
     CTCB200_CUDA(launch_fused(p, s, d_loss, loss_out, grad_logits, W, st));
     return CTCB200_OK;
   }

@@ -42,7 +42,7 @@ int ctcb200_host_create(const ctcb200_desc* desc, int device, int num_slices, ct
   const int slice_b = desc->B > 0 ? (desc->B + num_slices - 1) / num_slices : 0;
   ctcb200_desc sd = *desc;
   sd.B = slice_b;
-  const size_t ws_bytes = ctcb200_workspace_bytes(&sd, CTCB200_WS_LOSS_GRAD);
+  const size_t ws_bytes = ctcb200_workspace_bytes(&sd, CTCB200_WS_LOSS_GRAD_LOGITS);
   if (ws_bytes == 0 && slice_b > 0) return CTCB200_ERR_BAD_DESCRIPTOR;
   ctcb200_host_ctx* c = new (std::nothrow) ctcb200_host_ctx();
   if (c == nullptr) return CTCB200_ERR_CUDA;
