@@ -67,6 +67,7 @@ extern "C" {
  * serves the shape this is about a third of CTCB200_WS_LOSS_GRAD (no gathered rows, one state tensor instead of two);
  * otherwise the two are equal.  A workspace sized with CTCB200_WS_LOSS_GRAD is always accepted as well. */
 #define CTCB200_WS_LOSS_GRAD_LOGITS 3
+#define CTCB200_WS_HVP_LOGITS 4       /* ctcb200_hvp_logits */
 
 typedef struct ctcb200_desc {
   int32_t B;       /* batch size                      (>= 0) */
@@ -139,6 +140,17 @@ int ctcb200_hessian(const ctcb200_desc* desc, const float* logits, const int32_t
 int ctcb200_hvp(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
                 const int32_t* label_length, const int32_t* logit_length, const float* d_gradient, float* out,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Hessian-vector product w.r.t. the LOGITS: out[b] = d_loss[b] * (d2 loss[b] / d logits2) v[b], the quantity TF autodiff
+ * produces when tape.gradient is taken of the first derivative of classic_ctc_loss / simplified_ctc_loss
+ * (gradient_fn.backprop base_loss.py:167-173 chained through logit_to_logproba tools.py:27-40; README.md:58-71).
+ * Matrix-free: neither the [B,T,V,T,V] Hessian nor gamma is formed.  `desc` must describe logits (no
+ * CTCB200_INPUT_LOGPROBAS); d_loss may be NULL (ones); workspace sized with CTCB200_WS_HVP_LOGITS.
+ */
+int ctcb200_hvp_logits(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                       const int32_t* label_length, const int32_t* logit_length, const float* d_loss, const float* v,
+                       float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Host-buffer convenience path (what a framework without device tensors, or the end-to-end benchmark, calls):

@@ -283,6 +283,28 @@ def test_hessian_matches_oracle(variant, k4, monkeypatch):
 
 
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_hvp_wrt_logits_matches_oracle(variant):
+    """ctcb200_hvp_logits: d_loss * (d2 loss / d logits2) v, matrix-free with the log-softmax chain of SURVEY.md appendix B
+    (what tape.gradient of the first derivative returns in README.md:58-71), vs the oracle's dense Hessian w.r.t. logits."""
+    from tf_seq2seq_losses_b200 import _lib
+    for (B, T, V, L, seed) in [(2, 5, 3, 2, 0), (3, 9, 6, 4, 1), (2, 30, 70, 10, 2)]:
+        logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
+        data, lp = orc.ctc_loss_data(labels, logits, ll, tl, 0, variant)
+        H = orc.hessian_logits(data, lp, data.hessian if T <= 9 else data.hessian_fast())
+        rng = np.random.default_rng(seed)
+        v = rng.standard_normal((B, T, V)).astype(np.float32)
+        dl = rng.standard_normal((B,)).astype(np.float32)
+        want = dl[:, None, None] * np.einsum("btkuj,buj->btk", H, v)
+        x, lab = _cuda(logits, torch.float32), _cuda(labels, torch.int32)
+        desc = _lib.make_desc(x, lab, 0, variant, int(ll.max()) + 1, 0)
+        got = _lib.hvp_logits(desc, x, lab, _cuda(ll, torch.int32), _cuda(tl, torch.int32), _cuda(v), _cuda(dl))
+        assert np.max(np.abs(got.cpu().numpy() - want)) <= 2e-4          # sums T*V terms of |v| ~ 1
+        # rows at or beyond logit_length are exactly zero
+        mask = np.arange(T)[None, :] >= tl[:, None]
+        assert np.array_equal(got.cpu().numpy()[mask], np.zeros_like(want[mask]))
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
 def test_gamma_matches_oracle(variant):
     """ClassicCtcLossData.gamma / SimplifiedCtcLossData.gamma vs the literal oracle unfolding; gamma[:,0,0(,0)] == alpha
     (tests/test_hessian.py:62-87); -inf below the time diagonal, identity on it (classic_ctc_loss.py:204-213,286-308)."""

@@ -16,7 +16,7 @@ SIMPLIFIED = 1
 INPUT_LOGPROBAS = 1
 FORCE_STAGED = 2
 FORCE_FUSED = 4
-WS_LOSS_GRAD, WS_STATES, WS_HESSIAN, WS_LOSS_GRAD_LOGITS = 0, 1, 2, 3
+WS_LOSS_GRAD, WS_STATES, WS_HESSIAN, WS_LOSS_GRAD_LOGITS, WS_HVP_LOGITS = 0, 1, 2, 3, 4
 MAX_STATES = 512
 MAX_TOKENS = 32768
 
@@ -26,7 +26,7 @@ _LIB_PATH = os.environ.get("CTCB200_LIB", os.path.join(os.path.dirname(os.path.a
 EXPORTED_SYMBOLS = (
     "ctcb200_version", "ctcb200_strerror", "ctcb200_stage_names", "ctcb200_launches_per_call",
     "ctcb200_workspace_bytes", "ctcb200_loss_grad", "ctcb200_states",
-    "ctcb200_hessian", "ctcb200_hvp", "ctcb200_gamma", "ctcb200_host_create", "ctcb200_host_loss_grad",
+    "ctcb200_hessian", "ctcb200_hvp", "ctcb200_hvp_logits", "ctcb200_gamma", "ctcb200_host_create", "ctcb200_host_loss_grad",
     "ctcb200_host_grad_device_ptr", "ctcb200_host_destroy",
 )
 
@@ -76,6 +76,8 @@ def load() -> ctypes.CDLL:
     lib.ctcb200_gamma.argtypes = [dp, fp, i32p, i32p, i32p, fp, vp, ctypes.c_size_t, vp]
     lib.ctcb200_hvp.restype = ctypes.c_int
     lib.ctcb200_hvp.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, vp, ctypes.c_size_t, vp]
+    lib.ctcb200_hvp_logits.restype = ctypes.c_int
+    lib.ctcb200_hvp_logits.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, fp, vp, ctypes.c_size_t, vp]
     lib.ctcb200_host_create.restype = ctypes.c_int
     lib.ctcb200_host_create.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
     lib.ctcb200_host_loss_grad.restype = ctypes.c_int
@@ -203,6 +205,22 @@ def hvp(desc: Desc, logits, labels, label_length, logit_length, d_gradient):
             check(load().ctcb200_hvp(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
                                      _ptr(logit_length), _ptr(d_gradient), _ptr(out), _ptr(ws), ws.numel(),
                                      _stream(dev)))
+    return out
+
+
+def hvp_logits(desc: Desc, logits, labels, label_length, logit_length, v, d_loss=None):
+    """ctcb200_hvp_logits: d_loss[b] * (d2 loss[b] / d logits2) v[b] -> [B,T,V], matrix-free, log-softmax chain included."""
+    _require_cuda(logits, "logits")
+    dev = logits.device
+    out = torch.zeros((desc.B, desc.T, desc.V), dtype=torch.float32, device=dev)
+    ws = _workspace(desc, WS_HVP_LOGITS, dev)
+    if desc.B > 0 and desc.T > 0:
+        v = v.to(torch.float32).contiguous()
+        d_loss = None if d_loss is None else d_loss.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            check(load().ctcb200_hvp_logits(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
+                                            _ptr(logit_length), _ptr(d_loss), _ptr(v), _ptr(out), _ptr(ws), ws.numel(),
+                                            _stream(dev)))
     return out
 
 

@@ -230,19 +230,12 @@ class _FusedGradFn(torch.autograd.Function):
     def backward(ctx, v):
         logits, d_loss, grad = ctx.saved_tensors
         labels, label_length, logit_length = ctx.aux
-        x = logits.detach().contiguous()
-        logprobas = torch.log_softmax(x, dim=2)
-        p = torch.exp(logprobas)
-        lp_desc = _lib.Desc(ctx.desc.B, ctx.desc.T, ctx.desc.V, ctx.desc.Lw, ctx.desc.blank, ctx.desc.variant,
-                            ctx.desc.U, _lib.INPUT_LOGPROBAS)
-        # J v with J = d logproba / d logits = I - 1 p^T (per frame)
-        w = v - (p * v).sum(dim=2, keepdim=True)
-        y = _lib.hvp(lp_desc, logprobas, labels, label_length, logit_length, w.contiguous())
-        _, _, g = _lib.loss_grad(lp_desc, logprobas, labels, label_length, logit_length, want_grad_logits=False,
-                                 want_grad_logprobas=True)
-        s = g.sum(dim=2, keepdim=True)
-        hv = y - p * y.sum(dim=2, keepdim=True) - s * (p * v - p * (p * v).sum(dim=2, keepdim=True))
-        d_logits = d_loss[:, None, None] * hv if ctx.needs_input_grad[0] else None
+        d_logits = None
+        if ctx.needs_input_grad[0]:
+            # (d2 loss / d logits2) v = J^T H J v - s (p.v - p p^T v), J = I - 1 p^T per frame: one library call
+            # (ctcb200_hvp_logits: K1, K2, K3, hvp_pre, K4<HVP>, hvp_post)
+            d_logits = _lib.hvp_logits(ctx.desc, logits.detach().contiguous(), labels, label_length, logit_length, v,
+                                       d_loss)
         d_d_loss = (v * grad).sum(dim=(1, 2)) if ctx.needs_input_grad[1] else None
         return d_logits, d_d_loss, None, None, None
 

@@ -48,6 +48,7 @@ static size_t carve(const Problem& p, int what, bool fused_only, char* base, Scr
   const size_t o_ld = c.take((size_t)p.B * 8);
   size_t o_g = 0;
   if (what == CTCB200_WS_HESSIAN) o_g = c.take(rows * p.V * 4);
+  if (what == CTCB200_WS_HVP_LOGITS) o_g = c.take(3 * align256(rows * p.V * 4) + align256(rows * 4));   // g, w, y, p.v
   if (base != nullptr) {
     s->rowlse = reinterpret_cast<float*>(base + o_lse);
     s->h = reinterpret_cast<float*>(base + o_h);
@@ -58,7 +59,7 @@ static size_t carve(const Problem& p, int what, bool fused_only, char* base, Scr
     s->ca = reinterpret_cast<double*>(base + o_ca);
     s->cb = reinterpret_cast<double*>(base + o_cb);
     s->lossd = reinterpret_cast<double*>(base + o_ld);
-    if (grad_tmp) *grad_tmp = what == CTCB200_WS_HESSIAN ? reinterpret_cast<float*>(base + o_g) : nullptr;
+    if (grad_tmp) *grad_tmp = (what == CTCB200_WS_HESSIAN || what == CTCB200_WS_HVP_LOGITS) ? reinterpret_cast<float*>(base + o_g) : nullptr;
   }
   return c.off;
 }
@@ -146,7 +147,7 @@ int ctcb200_launches_per_call(const ctcb200_desc* desc) {
 size_t ctcb200_workspace_bytes(const ctcb200_desc* desc, int what) {
   Problem p;
   if (make_problem(desc, &p) != CTCB200_OK) return 0;
-  if (what < CTCB200_WS_LOSS_GRAD || what > CTCB200_WS_LOSS_GRAD_LOGITS) return 0;
+  if (what < CTCB200_WS_LOSS_GRAD || what > CTCB200_WS_HVP_LOGITS) return 0;
   return carve(p, what, fused_only_ws(desc, p, what), nullptr, nullptr, nullptr);
 }
 
@@ -240,6 +241,28 @@ int ctcb200_hvp(const ctcb200_desc* desc, const float* logits, const int32_t* la
   CTCB200_CUDA(launch_recursion(p, s, s.loss, false, st));
   CTCB200_CUDA(launch_grad(p, s, nullptr, nullptr, gtmp, st));
   CTCB200_CUDA(launch_hessian(p, s, gtmp, nullptr, d_gradient, out, st));
+  return CTCB200_OK;
+}
+
+int ctcb200_hvp_logits(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                       const int32_t* label_length, const int32_t* logit_length, const float* d_loss, const float* v,
+                       float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (desc != nullptr && (desc->flags & CTCB200_INPUT_LOGPROBAS)) return CTCB200_ERR_BAD_DESCRIPTOR;   // wants logits
+  Problem p; Scratch s; float* tmp = nullptr;
+  int rc = check_common(desc, &p, CTCB200_WS_HVP_LOGITS, logits, labels, label_length, logit_length, workspace,
+                        workspace_bytes, &s, &tmp);
+  if (rc != CTCB200_OK) return rc;
+  if (p.B == 0 || p.T == 0) return CTCB200_OK;
+  if (v == nullptr || out == nullptr) return CTCB200_ERR_NULL_POINTER;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = align256((size_t)p.B * p.T * p.V * 4) / 4;
+  float *g = tmp, *w = tmp + n, *y = tmp + 2 * n, *pv = tmp + 3 * n;
+  CTCB200_CUDA(launch_softmax_gather(p, s, st));
+  CTCB200_CUDA(launch_recursion(p, s, s.loss, false, st));
+  CTCB200_CUDA(launch_grad(p, s, nullptr, nullptr, g, st));
+  CTCB200_CUDA(launch_hvp_pre(p, s, v, w, pv, st));
+  CTCB200_CUDA(launch_hessian(p, s, g, nullptr, w, y, st));
+  CTCB200_CUDA(launch_hvp_post(p, s, v, y, g, pv, d_loss, out, st));
   return CTCB200_OK;
 }
 

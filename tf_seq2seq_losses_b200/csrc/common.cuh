@@ -130,6 +130,9 @@ cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss
                          cudaStream_t st);
 cudaError_t launch_export_states(const Problem& p, const Scratch& s, float* alpha, float* beta, cudaStream_t st);
 cudaError_t launch_gamma(const Problem& p, const Scratch& s, float* gamma, cudaStream_t st);
+cudaError_t launch_hvp_pre(const Problem& p, const Scratch& s, const float* v, float* w, float* pv, cudaStream_t st);
+cudaError_t launch_hvp_post(const Problem& p, const Scratch& s, const float* v, const float* y, const float* g,
+                            const float* pv, const float* d_loss, float* out, cudaStream_t st);
 cudaError_t launch_hessian(const Problem& p, const Scratch& s, const float* g, float* hessian,
                            const float* d_gradient, float* hvp_out, cudaStream_t st);
 

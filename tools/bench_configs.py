@@ -78,7 +78,33 @@ def hessian_case(B, T, V, L):
     print(f"{'hvp (matrix-free) same shape':46s} {'k1,k2,k3,k4_hessian<hvp>':40s} {timed(fn2)*1e3:9.1f} us")
 
 
+def readme_case(variant, name):
+    """The reference's own benchmark shape (tests/benchmark.py:41-56, tests/common.py:53-104): B=256, T=255, V=32,
+    labels [256,255], logit_length ~ U[127,255), label_length ~ U[63,127); forward only and loss + gradient, through the
+    public Python face like the reference's benchmark (README.md:18-24 reports 0.138 / 0.28 classic and 0.0531 / 0.119
+    simplified on a GTX 970, in its unit per 256-sample batch)."""
+    B, T, V = 256, 255, 32
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn((B, T, V), generator=g).cuda()
+    tl = torch.randint(T // 2, T, (B,), generator=g, dtype=torch.int32).cuda()
+    ll = torch.randint(T // 4, T // 2, (B,), generator=g, dtype=torch.int32).cuda()
+    labels = torch.randint(1, V, (B, T), generator=g, dtype=torch.int32).cuda()
+    fn = pkg.classic_ctc_loss if variant == _lib.CLASSIC else pkg.simplified_ctc_loss
+    U = int(ll.max().item())
+    fwd = lambda: fn(labels, logits, ll, tl, 0, max_label_length=U)
+    x = logits.clone().requires_grad_(True)
+
+    def fwd_bwd():
+        x.grad = None
+        fn(labels, x, ll, tl, 0, max_label_length=U).sum().backward()
+
+    ms_f, ms_g = timed(fwd), timed(fwd_bwd)
+    print(f"{name:46s} forward {ms_f*1e3:8.1f} us   loss+gradient {ms_g*1e3:8.1f} us   ({B/ms_g*1e3:9.0f} samples/s)")
+
+
 if __name__ == "__main__":
+    readme_case(_lib.CLASSIC, "README benchmark classic B=256 T=255 V=32")
+    readme_case(_lib.SIMPLIFIED, "README benchmark simplified B=256 T=255 V=32")
     loss_grad_case("cfg1 classic B=32 T=500 V=29 L=100", 32, 500, 29, 100, _lib.CLASSIC, False)
     loss_grad_case("cfg1 ragged", 32, 500, 29, 100, _lib.CLASSIC, False, ragged=True)
     loss_grad_case("cfg2 simplified B=256 T=1000 V=1024 L=200", 256, 1000, 1024, 200, _lib.SIMPLIFIED, False)
