@@ -7,8 +7,8 @@
 //     occ[t,k]          = exp(loss + c[t,k])                              (= -gradient)
 //     grad_logprobas    = -d_loss * occ
 //     grad_logits[t,k]  = d_loss * (softmax[t,k] * sum_k' occ[t,k'] - occ[t,k])
-// One CTA = kRows consecutive frames of one utterance.  The CTA builds the utterance's token -> slot map once in
-// shared memory (slot = first label position carrying that token; blank has its own slot), each warp then owns
+// One CTA = k3_rows(p) consecutive frames of one utterance.  The CTA builds the utterance's token -> slot map once in
+// shared memory (slot = a label position carrying that token; blank has its own slot), each warp then owns
 // whole frames: it accumulates the <= U+1 per-state occupancies into its slot array with shared-memory atomics
 // and streams the logits row once (128-bit loads / stores) to produce the dense output row.
 #include "common.cuh"
@@ -17,7 +17,14 @@
 namespace ctcb200 {
 
 constexpr int kK3Warps = 8;
-constexpr int kK3Rows = 16;
+// Frames per CTA.  The per-utterance tables are rebuilt by every CTA, so narrow vocabularies (cheap rows) take longer
+// tiles -- as long as that still leaves four CTAs for each of the 148 SMs.
+__host__ __device__ inline int k3_rows(const Problem& p) {
+  if (p.V >= 512) return 16;
+  for (int rows = 64; rows > 16; rows >>= 1)
+    if ((long long)p.B * ((p.T + rows - 1) / rows) >= 4 * 148) return rows;
+  return 16;
+}
 __device__ __forceinline__ void zero_row(float* dst, int V, int lane) {
   if (dst == nullptr) return;
   if (((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -40,6 +47,7 @@ __global__ void __launch_bounds__(kK3Warps * kWarp)
   float* acc_all = reinterpret_cast<float*>(toks + p.Upad);
   const int acc_pitch = p.Upad + kWarp;     // slots 0..Upad-1 = label positions, slot Upad = blank
 
+  const int kK3Rows = k3_rows(p);
   const int tiles = (p.T + kK3Rows - 1) / kK3Rows;
   const int b = blockIdx.x / tiles, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t_begin = (blockIdx.x % tiles) * kK3Rows, t_end = min(p.T, t_begin + kK3Rows);
@@ -133,6 +141,7 @@ cudaError_t launch_grad(const Problem& p, const Scratch& s, const float* d_loss,
                         float* grad_logprobas, cudaStream_t st) {
   if (p.B == 0 || p.T == 0 || (grad_logits == nullptr && grad_logprobas == nullptr)) return cudaSuccess;
   const size_t smem = grad_smem_bytes(p);
+  const int kK3Rows = k3_rows(p);
   const unsigned grid = (unsigned)(((p.T + kK3Rows - 1) / kK3Rows) * (long long)p.B);
   cudaError_t e;
   if (p.variant == CTCB200_CLASSIC) {

@@ -38,22 +38,19 @@ __device__ __forceinline__ int pos_prev(int pos, int lane, int ns) {
 
 // Shared-memory tables of one utterance, built once per CTA:
 //   toks[l]  cleaned label (base_loss.py:395-418), l in [0, Upad): blank for l >= label_length
-//   map[k]   token -> slot (first label position carrying k); blank -> slot Upad; kNoSlot for tokens not in the label
+//   map[k]   token -> slot (one of the label positions carrying k); blank -> slot Upad; kNoSlot for tokens not in the label
 __device__ __forceinline__ void build_utterance_tables(const Problem& p, int b, int L, int* toks,
                                                        unsigned short* map, int Vpad) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   for (int k = tid; k < Vpad; k += nthr) map[k] = kNoSlot;
   for (int l = tid; l < p.Upad; l += nthr) toks[l] = utt_token(p, b, l, L);
   __syncthreads();
+  // Any label position carrying the token serves as its slot: the racing 16-bit stores leave exactly one of them, and
+  // every reader comes after the barrier.  (A compare-and-swap minimum was 4x slower for character vocabularies, where
+  // a hundred labels compete for thirty tokens.)
   for (int l = tid; l < L; l += nthr) {
     const int tok = toks[l];
-    if (tok < 0 || tok >= p.V) continue;
-    unsigned short old = map[tok];
-    while (old > (unsigned short)l) {                    // 16-bit atomic min via CAS
-      const unsigned short assumed = old;
-      old = atomicCAS(&map[tok], assumed, (unsigned short)l);
-      if (old == assumed) break;
-    }
+    if (tok >= 0 && tok < p.V) map[tok] = (unsigned short)l;
   }
   __syncthreads();
   if (tid == 0) map[p.blank] = (unsigned short)p.Upad;   // the blank column is overridden (blank_mask tf.where)
