@@ -300,10 +300,13 @@ __device__ __forceinline__ void fused_zero_row(float* dst, int V, int lane, bool
 
 // ---- recursion warp, one phase ---------------------------------------------------------------------------------------
 // Frame i of the phase is frame t = t_first + i * t_step of the utterance.  SIDE 0 = alpha (forward), 1 = beta.
-template <int NS, bool CLASSIC, int SIDE, bool PHASE_B>
+// One rolled loop serves both phases (`phase_b` is a warp-uniform runtime flag) and the renormalisation cadence is
+// counted at run time: unrolling four frames per (side, phase) instantiation made the classic kernel 156 KB (U = 201)
+// to 253 KB (U = 401) of SASS, more than the instruction cache holds for ten warps in different roles.
+template <int NS, bool CLASSIC, int SIDE>
 __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int b, int count,
-                                          int t_first, int t_step, float* v0, float* v1, double& c,
-                                          const LabelBits<NS>& lb, int lane, long long* tm) {
+                                       int t_first, int t_step, bool phase_b, float* v0, float* v1, double& c,
+                                       const LabelBits<NS>& lb, int lane, long long* tm) {
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const int R = f.R;
   float m_pend = kNegInf;
@@ -312,53 +315,50 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
   float* g_state = a.stateT + ((size_t)b * a.p.T + t_first) * (size_t)(S * kUpad);
   double* g_off = a.coff + (size_t)b * a.p.T + t_first;
   const ptrdiff_t g_step = (ptrdiff_t)t_step * (S * kUpad);
-  for (int i0 = 0; i0 < count; i0 += kFusedGroup) {
+#pragma unroll 1
+  for (int i = 0; i < count; ++i) {
+    TIMED(3, mbar_wait(sv.full_d + slot, use_par));          // the frame's inputs are in the ring
+    float d[NS];
+    const float* dsrc = sv.ringd + slot * kUpad;
 #pragma unroll
-    for (int k = 0; k < kFusedGroup; ++k) {
-      const int i = i0 + k;
-      if (i < count) {
-        TIMED(3, mbar_wait(sv.full_d + slot, use_par));          // the frame's inputs are in the ring
-        float d[NS];
-        const float* dsrc = sv.ringd + slot * kUpad;
+    for (int j = 0; j < NS; ++j) d[j] = dsrc[j * kWarp + lane];
+    const float h = sv.ringh[slot];
+    if (!phase_b) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sv.empty + slot);             // ring slot may be refilled
+      // pre-step state -> global scratch for the other side's phase B
 #pragma unroll
-        for (int j = 0; j < NS; ++j) d[j] = dsrc[j * kWarp + lane];
-        const float h = sv.ringh[slot];
-        if (!PHASE_B) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sv.empty + slot);             // ring slot may be refilled
-          // pre-step state -> global scratch for the other side's phase B
-#pragma unroll
-          for (int j = 0; j < NS; ++j) {
-            stg_keep(g_state + j * kWarp + lane, v0[j]);
-            if (CLASSIC) stg_keep(g_state + kUpad + j * kWarp + lane, v1[j]);
-          }
-          if (lane == 0) *g_off = c;
-          g_state += g_step;
-          g_off += t_step;
-        } else {
-          if (i >= R) TIMED(6, mbar_wait(sv.empty + slot, use_par ^ 1u));   // previous frame of the slot is finished
-          float* dst = sv.rings + slot * (S * kUpad);
-#pragma unroll
-          for (int j = 0; j < NS; ++j) {
-            dst[j * kWarp + lane] = v0[j];
-            if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
-          }
-          if (lane == 0) sv.ringc[slot] = c;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sv.full_s + slot);
-        }
-        if (SIDE == 0) {
-          if (CLASSIC) alpha_step_classic<NS>(v0, v1, d, h, lane, lb);
-          else alpha_step_simplified<NS>(v0, d, h, lane);
-        } else {
-          if (CLASSIC) beta_step_classic<NS>(v0, v1, d, h, lane, lb);
-          else beta_step_simplified<NS>(v0, d, h, lane);
-        }
-        if (k == 0) m_pend = state_max<NS, CLASSIC>(v0, v1);
-        if (k == 2) apply_offset<NS, CLASSIC>(v0, v1, m_pend, c);
-        if (++slot == R) { slot = 0; use_par ^= 1u; }
+      for (int j = 0; j < NS; ++j) {
+        stg_keep(g_state + j * kWarp + lane, v0[j]);
+        if (CLASSIC) stg_keep(g_state + kUpad + j * kWarp + lane, v1[j]);
       }
+      if (lane == 0) *g_off = c;
+      g_state += g_step;
+      g_off += t_step;
+    } else {
+      if (i >= R) TIMED(6, mbar_wait(sv.empty + slot, use_par ^ 1u));   // previous frame of the slot is finished
+      float* dst = sv.rings + slot * (S * kUpad);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        dst[j * kWarp + lane] = v0[j];
+        if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
+      }
+      if (lane == 0) sv.ringc[slot] = c;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sv.full_s + slot);
     }
+    if (SIDE == 0) {
+      if (CLASSIC) alpha_step_classic<NS>(v0, v1, d, h, lane, lb);
+      else alpha_step_simplified<NS>(v0, d, h, lane);
+    } else {
+      if (CLASSIC) beta_step_classic<NS>(v0, v1, d, h, lane, lb);
+      else beta_step_simplified<NS>(v0, d, h, lane);
+    }
+    // lagged offset renormalisation: the warp maximum taken after frame 4n is subtracted two frames later
+    const int k = i & (kFusedGroup - 1);
+    if (k == 0) m_pend = state_max<NS, CLASSIC>(v0, v1);
+    else if (k == 2) apply_offset<NS, CLASSIC>(v0, v1, m_pend, c);
+    if (++slot == R) { slot = 0; use_par ^= 1u; }
   }
 }
 
@@ -745,49 +745,57 @@ __global__ void __launch_bounds__(2 * ((CLASSIC ? 3 : kMaxWorkers) + 1) * kWarp,
     }
   }
 
-  // ------------------------------------------------ phase A ------------------------------------------------------------
-  {
-    const int cnt = (side == 0) ? M : n_t - M, tf = (side == 0) ? 0 : n_t - 1, ts = (side == 0) ? 1 : -1;
-    if (role == 0) {
-      if (side == 0) rec_phase<NS, CLASSIC, 0, false>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
-      else rec_phase<NS, CLASSIC, 1, false>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
-    } else {
-      worker_phase<NS, CLASSIC, false, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, tok_left, okm, ok_left, lane, tm);
-    }
-  }
-
+  // ------------------------------------------------ phase A, the middle, phase B -----------------------------------------
+  // One rolled loop over the two phases: each recursion routine is inlined once per side instead of once per (side,
+  // phase), which halves the instruction footprint of the recursion warps.
+  bool dead = false;                 // no feasible alignment: loss = +inf, zero gradient
+  double lossd_mid = 0.0;            // -log Z, known after phase A
 #ifdef CTCB200_FUSED_TIMING
-  tm[0] = clock64() - t_start;
-  const long long t_mid = clock64();
+  long long t_mid = 0;
 #endif
-  // ------------------------------------------------ the middle ---------------------------------------------------------
-  if (role == 0) {
-    float* dst = xch + side * (S * kUpad);
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      dst[j * kWarp + lane] = v0[j];
-      if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
+#pragma unroll 1
+  for (int ph = 0; ph < 2; ++ph) {
+    int cnt, tf;
+    if (ph == 0) {
+      cnt = (side == 0) ? M : n_t - M;
+      tf = (side == 0) ? 0 : n_t - 1;
+    } else {
+      cnt = (side == 0) ? n_t - M : M;
+      tf = (side == 0) ? M : M - 1;
     }
-    if (lane == 0) xoff[side] = c;
-  }
-  __syncthreads();     // also makes phase A's global scratch visible to the whole CTA
-  if (tid == 0) reset_sync_state();
-  LseAcc zacc;
-  for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(xch[q] + xch[S * kUpad + q]);
-  const float lz = zacc.warp_result();
-  const bool dead = (lz == kNegInf);                          // no feasible alignment: loss = +inf, zero gradient
-  const double lossd_mid = -((double)lz + xoff[0] + xoff[1]);  // -log Z
-  __syncthreads();
-
-  // ------------------------------------------------ phase B ------------------------------------------------------------
-  if (!dead) {
-    const int cnt = (side == 0) ? n_t - M : M, tf = (side == 0) ? M : M - 1, ts = (side == 0) ? 1 : -1;
+    const int ts = (side == 0) ? 1 : -1;
     if (role == 0) {
-      if (side == 0) rec_phase<NS, CLASSIC, 0, true>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
-      else rec_phase<NS, CLASSIC, 1, true>(a, f, sv, b, cnt, tf, ts, v0, v1, c, lb, lane, tm);
+      if (side == 0) rec_phase<NS, CLASSIC, 0>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
+      else rec_phase<NS, CLASSIC, 1>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
+    } else if (ph == 0) {
+      worker_phase<NS, CLASSIC, false, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, tok_left, okm, ok_left, lane, tm);
     } else {
       worker_phase<NS, CLASSIC, true, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, tok_left, okm, ok_left, lane, tm);
     }
+    if (ph == 1) break;
+#ifdef CTCB200_FUSED_TIMING
+    tm[0] = clock64() - t_start;
+    t_mid = clock64();
+#endif
+    // ---------------------------------------------- the middle ---------------------------------------------------------
+    if (role == 0) {
+      float* dst = xch + side * (S * kUpad);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        dst[j * kWarp + lane] = v0[j];
+        if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
+      }
+      if (lane == 0) xoff[side] = c;
+    }
+    __syncthreads();     // also makes phase A's global scratch visible to the whole CTA
+    if (tid == 0) reset_sync_state();
+    LseAcc zacc;
+    for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(xch[q] + xch[S * kUpad + q]);
+    const float lz = zacc.warp_result();
+    dead = (lz == kNegInf);
+    lossd_mid = -((double)lz + xoff[0] + xoff[1]);
+    __syncthreads();
+    if (dead) break;
   }
 
 #ifdef CTCB200_FUSED_TIMING
