@@ -195,8 +195,8 @@ __device__ __forceinline__ float hsum4(float4 e) {
 
 // ---- shared-memory layout (one definition for host sizing and device carving) ---------------------------------------
 struct FusedLayout {
-  int W, R, SL, XA;         // workers per side, ring depth (= 2W), row buffers per worker, extra phase-A row buffers (0/1)
-  int off_xch, off_xoff, off_side0, total;
+  int W, R, SL, XA;         // workers per side, ring depth (W..2W), row buffers per worker, extra phase-A row buffers (0/1)
+  int off_xch, off_xoff, off_side0, total, xch_aliased;
   // offsets inside a side block
   int s_ctl, s_bar, s_row, s_aux, s_ringd, s_ringh, side_bytes;
   // offsets inside the aux block (phase B view)
@@ -208,15 +208,18 @@ __host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a *
 // Phase A is latency-bound by the bytes it keeps in flight, phase B needs the state ring and the stored-state staging
 // buffers instead: the `aux` block is the union of the two (XA extra row buffers per side in phase A; rings / ringc /
 // stbuf in phase B), which is what lets 4 workers x 3 row buffers fit next to a second CTA on the SM.
-__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL, int XA) {
+// R = ring depth in frames (>= W; 2W unless shared memory is short).  The exchange vectors of the middle (S*Upad floats
+// per side, used only between the phases) alias each side's own input ring when that is large enough.
+__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL, int XA, int R) {
   FusedLayout f;
   f.W = W;
-  f.R = 2 * W;
+  f.R = R;
   f.SL = SL;
   f.XA = XA;
   const int Vp = (V + 3) & ~3;
   int o = 0;
-  f.off_xch = o;  o += 2 * S * Upad * 4;
+  f.xch_aliased = (R >= S) ? 1 : 0;       // a side's exchange vector (S*Upad floats) fits its input ring (R*Upad floats)
+  f.off_xch = o;  o += f.xch_aliased ? 0 : 2 * S * Upad * 4;
   f.off_xoff = o; o += 2 * 8;
   o = fl_align(o, 128);
   int s = 0;
@@ -247,7 +250,7 @@ struct FusedArgs {
   const float* d_loss;  // [B] or null
   float* loss;          // [B]
   float* grad;          // [B,T,V]
-  int W, SL, XA;
+  int W, SL, XA, R;
   int tma;              // 1: rows move by 1-D TMA (V % 4 == 0, 16-byte aligned bases); 0: by 4-byte cp.async / plain stores
   long long* dbg;       // [B][warps][12] when built with CTCB200_FUSED_TIMING, else unused
 };
@@ -681,11 +684,11 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
 template <int NS, bool CLASSIC, bool TMA>
-__global__ void __launch_bounds__(2 * ((CLASSIC ? 3 : kMaxWorkers) + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
+__global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const Problem& p = a.p;
-  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA);
+  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA, a.R);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = f.W;
   // Warp -> (side, role); role 0 = recursion warp, 1..W = row workers.  Other placements were measured on B200 (the two
@@ -695,7 +698,10 @@ __global__ void __launch_bounds__(2 * ((CLASSIC ? 3 : kMaxWorkers) + 1) * kWarp,
   const int L = utt_label_len(p, b), n_t = utt_frames(p, b), M = n_t >> 1;
   const float dl = a.d_loss ? a.d_loss[b] : 1.0f;
 
-  float* xch = reinterpret_cast<float*>(smem + f.off_xch);
+  // exchange slot of a side (S*Upad floats): a dedicated buffer, or the head of that side's input ring (see fused_layout)
+  auto xch_of = [&](int s2) {
+    return reinterpret_cast<float*>(smem + (f.xch_aliased ? f.off_side0 + s2 * f.side_bytes + f.s_ringd : f.off_xch + s2 * (S * kUpad * 4)));
+  };
   double* xoff = reinterpret_cast<double*>(smem + f.off_xoff);
   const SideView sv = side_view(smem, f, side);
 
@@ -781,8 +787,10 @@ __global__ void __launch_bounds__(2 * ((CLASSIC ? 3 : kMaxWorkers) + 1) * kWarp,
     t_mid = clock64();
 #endif
     // ---------------------------------------------- the middle ---------------------------------------------------------
+    // Each recursion warp leaves its state vector in ITS OWN side's exchange slot.  When shared memory is short the slot
+    // aliases that side's input ring, which is idle by now: the warp has consumed every frame its workers produced.
     if (role == 0) {
-      float* dst = xch + side * (S * kUpad);
+      float* dst = xch_of(side);
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         dst[j * kWarp + lane] = v0[j];
@@ -793,7 +801,10 @@ __global__ void __launch_bounds__(2 * ((CLASSIC ? 3 : kMaxWorkers) + 1) * kWarp,
     __syncthreads();     // also makes phase A's global scratch visible to the whole CTA
     if (tid == 0) reset_sync_state();
     LseAcc zacc;
-    for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(xch[q] + xch[S * kUpad + q]);
+    {
+      const float *xa = xch_of(0), *xb = xch_of(1);
+      for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(xa[q] + xb[q]);
+    }
     const float lz = zacc.warp_result();
     dead = (lz == kNegInf);
     lossd_mid = -((double)lz + xoff[0] + xoff[1]);
@@ -831,7 +842,7 @@ cudaError_t launch_fused_variant(const FusedArgs& a, cudaStream_t st);
 
 template <int NS, bool CLASSIC, bool TMA>
 static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
-  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA);
+  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA, a.R);
   cudaError_t e = cudaFuncSetAttribute(kf_fused<NS, CLASSIC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, f.total);
   if (e != cudaSuccess) return e;
   kf_fused<NS, CLASSIC, TMA><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
