@@ -31,7 +31,7 @@ def _pkg():
 
 @pytest.fixture(params=["fused", "staged"])
 def kernel_path(request):
-    """The loss+gradient call has two device paths: the fused single-launch kernel (default for V >= 64 when its
+    """The loss+gradient call has two device paths: the fused single-launch kernel (default for V >= 64, or B >= 80, when its
     shared-memory plan fits) and the three staged kernels K1/K2/K3 (narrow vocabularies, oversized rows, and the
     states / Hessian entry points).  Both are forced in turn and must agree with the oracle on every shape."""
     from tf_seq2seq_losses_b200 import _lib

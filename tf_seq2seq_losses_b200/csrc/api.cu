@@ -68,10 +68,11 @@ static size_t carve(const Problem& p, int what, bool fused_only, char* base, Scr
 // and the bases are 16-byte aligned, by 4-byte cp.async otherwise).
 static int fused_workers(const ctcb200_desc* desc, const Problem& p) {
   if (desc->flags & CTCB200_FORCE_STAGED) return 0;
-  // Narrow vocabularies (character models, V < 64) are latency-bound on the T-step chain rather than on row traffic;
-  // there the staged recursion kernel, which streams the compact gathered rows, is measured faster (B=32 T=500 V=29:
-  // 191 us staged vs 239 us fused) unless the caller insists.
-  if (p.V < 64 && !(desc->flags & CTCB200_FORCE_FUSED)) return 0;
+  // Narrow vocabularies (character models, V < 64) in SMALL batches are latency-bound on the T-step chain rather than on
+  // row traffic; there the staged recursion kernel, which streams the compact gathered rows, is faster (B=32 T=500 V=29:
+  // 183 us staged vs 232 us fused).  From about 80 utterances on the fused kernel wins again because the staged gradient
+  // writer grows with B while the fused kernel still fits one wave (B=256 T=255 V=32: 136 us fused vs 257 us staged).
+  if (p.V < 64 && p.B < 80 && !(desc->flags & CTCB200_FORCE_FUSED)) return 0;
   return fused_pick_workers(p);
 }
 
