@@ -36,7 +36,7 @@ __device__ __forceinline__ void zero_row(float* dst, int V, int lane) {
   }
 }
 
-template <bool CLASSIC>
+template <int NS, bool CLASSIC>
 __global__ void __launch_bounds__(kK3Warps * kWarp)
     k3_grad(Problem p, Scratch s, const float* __restrict__ d_loss, float* __restrict__ grad_logits,
             float* __restrict__ grad_logprobas) {
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kK3Warps * kWarp)
     // loss + offset of alpha[t] + offset of beta[t+1]: a small number, formed in double
     const size_t crow = (size_t)b * (p.T + 1) + t;
     const float lossb = (float)(lossd + s.ca[crow] + s.cb[crow + 1]);
-    const float occ_sum = row_occupancies<CLASSIC>(p, L, lane, A, Bn, s.dT + row * p.Upad, s.h[row], lossb, toks,
-                                                   map, acc);
+    const float occ_sum = row_occupancies_t<NS, CLASSIC>(p, L, lane, A, Bn, s.dT + row * p.Upad, s.h[row], lossb, toks,
+                                                         map, acc);
 
     // dense row
     const float* x = p.logits + row * p.V;
@@ -137,25 +137,41 @@ size_t grad_smem_bytes(const Problem& p) {
          (size_t)kK3Warps * (p.Upad + kWarp) * sizeof(float);
 }
 
-cudaError_t launch_grad(const Problem& p, const Scratch& s, const float* d_loss, float* grad_logits,
-                        float* grad_logprobas, cudaStream_t st) {
-  if (p.B == 0 || p.T == 0 || (grad_logits == nullptr && grad_logprobas == nullptr)) return cudaSuccess;
+template <int NS>
+static cudaError_t launch_k3_ns(const Problem& p, const Scratch& s, const float* d_loss, float* grad_logits,
+                                float* grad_logprobas, cudaStream_t st) {
   const size_t smem = grad_smem_bytes(p);
   const int kK3Rows = k3_rows(p);
   const unsigned grid = (unsigned)(((p.T + kK3Rows - 1) / kK3Rows) * (long long)p.B);
   cudaError_t e;
   if (p.variant == CTCB200_CLASSIC) {
     if (smem > 48 * 1024 &&
-        (e = cudaFuncSetAttribute(k3_grad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+        (e = cudaFuncSetAttribute(k3_grad<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
       return e;
-    k3_grad<true><<<grid, kK3Warps * kWarp, smem, st>>>(p, s, d_loss, grad_logits, grad_logprobas);
+    k3_grad<NS, true><<<grid, kK3Warps * kWarp, smem, st>>>(p, s, d_loss, grad_logits, grad_logprobas);
   } else {
     if (smem > 48 * 1024 &&
-        (e = cudaFuncSetAttribute(k3_grad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+        (e = cudaFuncSetAttribute(k3_grad<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
       return e;
-    k3_grad<false><<<grid, kK3Warps * kWarp, smem, st>>>(p, s, d_loss, grad_logits, grad_logprobas);
+    k3_grad<NS, false><<<grid, kK3Warps * kWarp, smem, st>>>(p, s, d_loss, grad_logits, grad_logprobas);
   }
   return cudaGetLastError();
+}
+
+cudaError_t launch_grad(const Problem& p, const Scratch& s, const float* d_loss, float* grad_logits,
+                        float* grad_logprobas, cudaStream_t st) {
+  if (p.B == 0 || p.T == 0 || (grad_logits == nullptr && grad_logprobas == nullptr)) return cudaSuccess;
+  switch (p.NS) {
+#define CTCB200_CASE(n) \
+  case n:               \
+    return launch_k3_ns<n>(p, s, d_loss, grad_logits, grad_logprobas, st);
+    CTCB200_CASE(1) CTCB200_CASE(2) CTCB200_CASE(3) CTCB200_CASE(4) CTCB200_CASE(5) CTCB200_CASE(6)
+    CTCB200_CASE(7) CTCB200_CASE(8) CTCB200_CASE(9) CTCB200_CASE(10) CTCB200_CASE(11) CTCB200_CASE(12)
+    CTCB200_CASE(13) CTCB200_CASE(14) CTCB200_CASE(15) CTCB200_CASE(16)
+#undef CTCB200_CASE
+    default:
+      return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace ctcb200

@@ -116,4 +116,75 @@ __device__ __forceinline__ float row_occupancies(const Problem& p, int L, int la
   return occ_sum;
 }
 
+// Same as row_occupancies with the states-per-lane count known at compile time: the loop over the lane's states unrolls
+// and every global load of the frame (alpha, beta, d: 3 to 5 per state) is issued before the first is consumed.  The
+// run-time-NS form above serialises them (load -> use -> next load), which left K3 waiting on L2 for most of its time
+// (ncu: long-scoreboard stall 8.6 per issued instruction at B=32 T=500 V=29).
+template <int NS, bool CLASSIC>
+__device__ __forceinline__ float row_occupancies_t(const Problem& p, int L, int lane, const float* A, const float* Bn,
+                                                   const float* d, float h, float lossb, const int* toks,
+                                                   const unsigned short* map, float* acc) {
+  constexpr int kUpad = NS * kWarp;
+  for (int i = lane; i <= kUpad; i += kWarp) acc[i] = 0.0f;
+  float a0[NS], a1[NS], b0[NS], b1[NS], dv[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int pos = j * kWarp + lane;
+    a0[j] = A[pos];
+    b0[j] = Bn[pos];
+    dv[j] = d[pos];
+    if (CLASSIC) {
+      a1[j] = A[kUpad + pos];
+      b1[j] = Bn[kUpad + pos];
+    }
+  }
+  // neighbours across lanes: state l+1 of the lane's last state, state l-1 of its first
+  float b_up = __shfl_down_sync(kFull, CLASSIC ? b1[0] : b0[0], 1);
+  if (lane == 31) b_up = kNegInf;
+  float d_left = __shfl_up_sync(kFull, dv[NS - 1], 1);
+  if (lane == 0) d_left = kNegInf;
+  __syncwarp();
+  LseAcc blank_acc;
+  float occ_sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int l = lane * NS + j;
+    if (l > L) continue;
+    const int tok = toks[l];
+    const unsigned short slot = (tok >= 0 && tok < p.V) ? map[tok] : kNoSlot;
+    if (!CLASSIC) {
+      blank_acc.add(a0[j] + b0[j]);
+      if (l < L) {
+        const float bnext = (j < NS - 1) ? b0[j < NS - 1 ? j + 1 : j] : b_up;
+        const float o = __expf(lossb + (a0[j] + dv[j] + bnext));
+        if (slot != kNoSlot && o > 0.0f) atomicAdd(&acc[slot], o);
+        occ_sum += (slot != kNoSlot && slot != p.Upad) ? o : 0.0f;
+      }
+    } else {
+      blank_acc.add(lse2(a0[j], a1[j]) + b0[j]);
+      const int tok_prev = tok_at(p, toks, l - 1);
+      if (l < L) {     // diagonal step emitting label[l]: any state of l -> open state of l+1
+        const float bnext = (j < NS - 1) ? b1[j < NS - 1 ? j + 1 : j] : b_up;
+        const float v1 = (tok == tok_prev) ? kNegInf : a1[j] + dv[j];
+        const float o = __expf(lossb + (lse2(a0[j] + dv[j], v1) + bnext));
+        if (slot != kNoSlot && o > 0.0f) atomicAdd(&acc[slot], o);
+        occ_sum += (slot != kNoSlot && slot != p.Upad) ? o : 0.0f;
+      }
+      if (l >= 1) {    // horizontal step re-emitting label[l-1]: open l -> open l
+        const unsigned short sp = (tok_prev >= 0 && tok_prev < p.V) ? map[tok_prev] : kNoSlot;
+        const float dprev = (j > 0) ? dv[j > 0 ? j - 1 : 0] : d_left;
+        const float o = __expf(lossb + (a1[j] + dprev + b1[j]));
+        if (sp != kNoSlot && o > 0.0f) atomicAdd(&acc[sp], o);
+        occ_sum += (sp != kNoSlot && sp != p.Upad) ? o : 0.0f;
+      }
+    }
+  }
+  const float occ_blank = __expf(lossb + (h + blank_acc.warp_result()));
+  occ_sum = warp_sum(occ_sum) + occ_blank;
+  __syncwarp();
+  if (lane == 0) acc[kUpad] = occ_blank;
+  __syncwarp();
+  return occ_sum;
+}
+
 }  // namespace ctcb200
