@@ -65,6 +65,30 @@ def test_error_strings_and_descriptor_validation():
     assert lib.ctcb200_stage_names(ctypes.byref(narrow)) == b"kf_fused"
 
 
+def test_workspace_classes_and_kernel_choice():
+    """Workspace sizing rules of include/ctc_b200.h (no kernel is launched): the training call's class is never larger
+    than the general one and shrinks when the fused kernel serves the shape; ctcb200_stage_names reports the device path
+    (fused from V >= 64, or from 80 utterances on for narrower vocabularies, unless forced)."""
+    lib = _lib.load()
+    ws = lambda d, w: lib.ctcb200_workspace_bytes(ctypes.byref(d), w)
+    names = lambda d: lib.ctcb200_stage_names(ctypes.byref(d)).decode()
+    north_star = _lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, 0)
+    assert names(north_star) == "kf_fused" and lib.ctcb200_launches_per_call(ctypes.byref(north_star)) == 1
+    assert ws(north_star, _lib.WS_LOSS_GRAD_LOGITS) * 2 < ws(north_star, _lib.WS_LOSS_GRAD)
+    assert ws(north_star, _lib.WS_HVP_LOGITS) > ws(north_star, _lib.WS_HESSIAN) > ws(north_star, _lib.WS_STATES)
+    assert ws(north_star, 5) == 0 and ws(north_star, -1) == 0
+    staged = _lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, _lib.FORCE_STAGED)
+    assert names(staged) == "k1_softmax_gather,k2_recursion,k3_grad"
+    assert ws(staged, _lib.WS_LOSS_GRAD_LOGITS) == ws(staged, _lib.WS_LOSS_GRAD)
+    small_char = _lib.Desc(32, 500, 29, 100, 0, _lib.CLASSIC, 101, 0)        # BASELINE configs[1]
+    big_char = _lib.Desc(256, 255, 32, 255, 0, _lib.CLASSIC, 127, 0)         # the reference's tests/benchmark.py shape
+    assert names(small_char).startswith("k1_") and names(big_char) == "kf_fused"
+    assert names(_lib.Desc(32, 500, 29, 100, 0, _lib.CLASSIC, 101, _lib.FORCE_FUSED)) == "kf_fused"
+    full_sweep = _lib.Desc(2048, 1600, 5000, 400, 0, _lib.CLASSIC, 401, 0)   # BASELINE configs[4] on one GPU
+    assert names(full_sweep) == "kf_fused"
+    assert ws(full_sweep, _lib.WS_LOSS_GRAD_LOGITS) + 2 * 2048 * 1600 * 5000 * 4 < 180e9      # fits one B200
+
+
 def test_python_face_has_no_cpu_fallback():
     import tf_seq2seq_losses_b200 as pkg
     logits = torch.zeros((1, 4, 3))
