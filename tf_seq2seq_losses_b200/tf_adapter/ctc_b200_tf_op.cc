@@ -61,7 +61,7 @@ class CtcB200LossGradOp : public tf::OpKernel {
     tf::Tensor* grad = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({d.B}), &loss));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, logits.shape(), &grad));
-    const size_t ws_bytes = ctcb200_workspace_bytes(&d, CTCB200_WS_LOSS_GRAD);
+    const size_t ws_bytes = ctcb200_workspace_bytes(&d, CTCB200_WS_LOSS_GRAD_LOGITS);
     OP_REQUIRES(ctx, ws_bytes > 0 || d.B == 0, tf::errors::InvalidArgument("ctc_b200: unsupported shape"));
     tf::Tensor ws;
     OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_UINT8, tf::TensorShape({static_cast<tf::int64>(ws_bytes + 256)}), &ws));
