@@ -12,7 +12,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tf_seq2seq_losses_b200 import _lib  # noqa: E402
 
-B, T, V, L = int(os.environ.get("CTCB200_TIMING_B", "256")), 1000, 1024, 200
+B = int(os.environ.get("CTCB200_TIMING_B", "256"))
+T, V, L = (int(x) for x in os.environ.get("CTCB200_TIMING_TVL", "1000,1024,200").split(","))
 variant = _lib.CLASSIC if (len(sys.argv) > 1 and sys.argv[1] == "classic") else _lib.SIMPLIFIED
 g = torch.Generator().manual_seed(0)
 logits = torch.randn((B, T, V), generator=g).cuda()
@@ -36,7 +37,7 @@ NS = (L + 1 + 31) // 32
 Upad = 32 * NS
 rows, srows = B * T, B * (T + 1) * S * Upad
 off = a256(rows * 4) * 2 + a256(rows * Upad * 4) + a256(srows * 4)       # byte offset of the beta scratch
-W = int(os.environ.get("CTCB200_FUSED_W", "4" if variant == _lib.SIMPLIFIED else "3"))
+W = int(os.environ.get("CTCB200_FUSED_W", "4"))        # workers per side the kernel picked (1 for V = 5000)
 warps = 2 * (W + 1)
 dbg = ws[off: off + B * warps * 12 * 8].view(torch.int64).reshape(B, warps, 12).cpu().numpy().astype(np.float64)
 names = ["phaseA", "phaseB", "tma_wait", "rec:d_wait|work:gather", "ccount_wait", "scount_wait", "rec:done_wait|work:stats", "state_cpasync_wait",
