@@ -1,4 +1,7 @@
-import ctypes, os, sys, torch
+"""Developer tool: default / forced-fused / forced-staged device time (and per-stage times of the staged path) for the
+narrow-vocabulary and fallback shapes; this is what the dispatch rule in csrc/api.cu (fused_workers) is tuned on.
+   python tools/exp_paths.py            (needs a B200)"""
+import ctypes, sys, torch
 sys.path.insert(0, '/root/repo')
 from tf_seq2seq_losses_b200 import _lib
 sys.path.insert(0, '/root/repo/tools')
