@@ -1,11 +1,18 @@
 """Developer tool: default / forced-fused / forced-staged device time (and per-stage times of the staged path) for the
 narrow-vocabulary and fallback shapes; this is what the dispatch rule in csrc/api.cu (fused_workers) is tuned on.
    python tools/exp_paths.py            (needs a B200)"""
-import ctypes, sys, torch
-sys.path.insert(0, '/root/repo')
-from tf_seq2seq_losses_b200 import _lib
-sys.path.insert(0, '/root/repo/tools')
-import bench_configs as bc
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from tf_seq2seq_losses_b200 import _lib  # noqa: E402
+import bench_configs as bc  # noqa: E402
+
+
 def case(name,B,T,V,L,variant,flags,ragged=False):
     g = torch.Generator().manual_seed(0)
     logits = torch.randn((B, T, V), generator=g).cuda()
