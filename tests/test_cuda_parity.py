@@ -193,6 +193,23 @@ def test_loss_and_gradient_match_oracle(shape, variant, kernel_path):
 
 
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_upstream_gradient_inside_the_kernels(variant, kernel_path):
+    """ctcb200_loss_grad with a d_loss vector (forward_fn.backprop, base_loss.py:150-153, done inside the kernels: the
+    scaled softmax pass and scatter of the fused kernel, the scale factor of K3), incl. negative, zero and unit weights."""
+    from tf_seq2seq_losses_b200 import _lib
+    for (B, T, V, L, seed) in [(6, 40, 70, 12, 3), (4, 33, 130, 9, 4)]:
+        logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
+        d_loss = np.array([1.0, -0.75, 0.0, 2.5, 1.0, 0.3][:B], dtype=np.float32)
+        want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, variant, d_loss=d_loss)
+        x, lab = _cuda(logits, torch.float32), _cuda(labels, torch.int32)
+        desc = _lib.make_desc(x, lab, 0, variant, int(ll.max()) + 1, _lib.DEFAULT_FLAGS)
+        loss, grad, _ = _lib.loss_grad(desc, x, lab, _cuda(ll, torch.int32), _cuda(tl, torch.int32), d_loss=_cuda(d_loss))
+        _loss_close(loss.cpu().numpy(), want_loss)
+        want_grad[np.isinf(want_loss)] = 0.0
+        assert np.max(np.abs(grad.cpu().numpy() - want_grad)) <= 3 * GRAD_ATOL_SHORT      # |d_loss| up to 2.5
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
 def test_undefined_inputs_do_not_fault(variant, kernel_path):
     """Inputs the reference leaves undefined: label_length > labels.shape[1] (the reference pads with
     the blank as a *real* label), a real label equal to the blank, labels >= V or negative, logit_length > T, negative
