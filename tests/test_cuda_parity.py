@@ -193,6 +193,26 @@ def test_loss_and_gradient_match_oracle(shape, variant, kernel_path):
 
 
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_narrow_vocabulary_large_batch_takes_the_fused_kernel(variant):
+    """Character-sized vocabularies are served by the staged kernels in small batches and by the fused kernel from 80
+    utterances on (csrc/api.cu: fused_workers); both choices, unforced, against the oracle -- V = 29 rows are not 16-byte
+    aligned (cp.async row mover), V = 32 rows are (TMA)."""
+    import ctypes
+    from tf_seq2seq_losses_b200 import _lib
+    for (B, T, V, L, seed, want_path) in [(96, 40, 29, 10, 5, "kf_fused"), (96, 40, 32, 10, 6, "kf_fused"),
+                                          (24, 40, 29, 10, 7, "k1_softmax_gather,k2_recursion,k3_grad")]:
+        logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
+        x, lab = _cuda(logits, torch.float32), _cuda(labels, torch.int32)
+        desc = _lib.make_desc(x, lab, 0, variant, int(ll.max()) + 1, 0)
+        assert _lib.load().ctcb200_stage_names(ctypes.byref(desc)).decode() == want_path
+        loss, grad, _ = _lib.loss_grad(desc, x, lab, _cuda(ll, torch.int32), _cuda(tl, torch.int32))
+        want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, variant)
+        _loss_close(loss.cpu().numpy(), want_loss)
+        want_grad[np.isinf(want_loss)] = 0.0
+        assert np.max(np.abs(grad.cpu().numpy() - want_grad)) <= GRAD_ATOL_SHORT
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
 def test_upstream_gradient_inside_the_kernels(variant, kernel_path):
     """ctcb200_loss_grad with a d_loss vector (forward_fn.backprop, base_loss.py:150-153, done inside the kernels: the
     scaled softmax pass and scatter of the fused kernel, the scale factor of K3), incl. negative, zero and unit weights."""
