@@ -310,14 +310,14 @@ template <int NS, bool CLASSIC, int SIDE>
 __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int b, int count,
                                        int t_first, int t_step, bool phase_b, float* v0, float* v1, double& c,
                                        const LabelBits<NS>& lb, int lane, long long* tm) {
-  constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
+  constexpr int S_ = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const int R = f.R;
   float m_pend = kNegInf;
   int slot = 0;                // i % R
   unsigned use_par = 0;        // (i / R) & 1: parity of this use of the slot
-  float* g_state = a.stateT + ((size_t)b * a.p.T + t_first) * (size_t)(S * kUpad);
+  float* g_state = a.stateT + ((size_t)b * a.p.T + t_first) * (size_t)(S_ * kUpad);
   double* g_off = a.coff + (size_t)b * a.p.T + t_first;
-  const ptrdiff_t g_step = (ptrdiff_t)t_step * (S * kUpad);
+  const ptrdiff_t g_step = (ptrdiff_t)t_step * (S_ * kUpad);
 #pragma unroll 1
   for (int i = 0; i < count; ++i) {
     TIMED(3, mbar_wait(sv.full_d + slot, use_par));          // the frame's inputs are in the ring
@@ -326,32 +326,39 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
 #pragma unroll
     for (int j = 0; j < NS; ++j) d[j] = dsrc[j * kWarp + lane];
     const float h = sv.ringh[slot];
+    // What the other side / the row workers need of the pre-step state.  Simplified: the state.  Classic: from alpha
+    // the diagonal carrier x[l] = rep[l] ? A[l,0] : lse(A[l,0], A[l,1]) and the open plane A[l,1]; from beta the open
+    // plane B[l,1] alone (the blank's occupancy is the complement of the others, so B[l,0] is never read) -- the beta
+    // rows are half as wide, and no worker ever recomputes a log-sum-exp of the state.
+    float S[NS], x[NS];
+    if (CLASSIC && SIDE == 0) alpha_classic_prepare<NS>(v0, v1, lb, S, x);
+    const float* out0 = !CLASSIC ? v0 : (SIDE == 0 ? x : v1);
     if (!phase_b) {
       __syncwarp();
       if (lane == 0) mbar_arrive(sv.empty + slot);             // ring slot may be refilled
-      // pre-step state -> global scratch for the other side's phase B
+      // -> global scratch for the other side's phase B
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        stg_keep(g_state + j * kWarp + lane, v0[j]);
-        if (CLASSIC) stg_keep(g_state + kUpad + j * kWarp + lane, v1[j]);
+        stg_keep(g_state + j * kWarp + lane, out0[j]);
+        if (CLASSIC && SIDE == 0) stg_keep(g_state + kUpad + j * kWarp + lane, v1[j]);
       }
       if (lane == 0) *g_off = c;
       g_state += g_step;
       g_off += t_step;
     } else {
       if (i >= R) TIMED(6, mbar_wait(sv.empty + slot, use_par ^ 1u));   // previous frame of the slot is finished
-      float* dst = sv.rings + slot * (S * kUpad);
+      float* dst = sv.rings + slot * (S_ * kUpad);
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        dst[j * kWarp + lane] = v0[j];
-        if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
+        dst[j * kWarp + lane] = out0[j];
+        if (CLASSIC && SIDE == 0) dst[kUpad + j * kWarp + lane] = v1[j];
       }
       if (lane == 0) sv.ringc[slot] = c;
       __syncwarp();
       if (lane == 0) mbar_arrive(sv.full_s + slot);
     }
     if (SIDE == 0) {
-      if (CLASSIC) alpha_step_classic<NS>(v0, v1, d, h, lane, lb);
+      if (CLASSIC) alpha_classic_finish<NS>(v0, v1, S, x, d, h, lane, lb);
       else alpha_step_simplified<NS>(v0, d, h, lane);
     } else {
       if (CLASSIC) beta_step_classic<NS>(v0, v1, d, h, lane, lb);
@@ -436,10 +443,11 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     if (PHASE_B) {
       // the other side's stored state for this frame: async copy now, consumed after the recursion catches up
       const float* src = a.stateT + ((size_t)b * p.T + t) * (size_t)(S * kUpad);
+      const int n16 = ((CLASSIC && side == 0) ? 1 : S) * (kUpad / 4);      // classic beta rows hold the open plane only
 #pragma unroll
       for (int k = 0; k < (S * kUpad / 4 + kWarp - 1) / kWarp; ++k) {
         const int cidx = k * kWarp + lane;
-        if (cidx < S * kUpad / 4) fused_cp_async16_keep(stb + 4 * cidx, src + 4 * cidx);
+        if (cidx < n16) fused_cp_async16_keep(stb + 4 * cidx, src + 4 * cidx);
       }
       fused_cp_async_commit();
       if (n + 1 < n_my) {
@@ -603,13 +611,13 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           if (!((okm >> j) & 1u)) occ[j] = 0.0f;
         }
       } else {
-        float a0[NS], a1[NS], b0[NS], b1[NS];
+        // alpha rows: plane 0 = x[l] (the diagonal carrier, see rec_phase), plane 1 = A[l,1]; beta rows: B[l,1]
+        float xa[NS], a1[NS], b1[NS];
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-          a0[j] = A[j * kWarp + lane];
+          xa[j] = A[j * kWarp + lane];
           a1[j] = A[kUpad + j * kWarp + lane];
-          b0[j] = Bn[j * kWarp + lane];
-          b1[j] = Bn[kUpad + j * kWarp + lane];
+          b1[j] = Bn[j * kWarp + lane];
         }
         float bx = __shfl_down_sync(kFull, b1[0], 1);
         if (lane == 31) bx = kNegInf;
@@ -617,11 +625,9 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
         if (lane == 0) d_left = kNegInf;
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-          const int tp = (j > 0) ? tok[j - 1] : tok_left;
-          const float sj = lse2(a0[j], a1[j]);
           const float bn = (j < NS - 1) ? b1[j + 1] : bx;
-          // diagonal step emitting label[l] (classic_ctc_loss.py:629-639); open -> open is barred on a repeat
-          occ[j] = ex2_approx((K + (dd[j] + ((tok[j] == tp) ? a0[j] : sj) + bn)) * kLog2e);
+          // diagonal step emitting label[l] (classic_ctc_loss.py:629-639); open -> open is barred on a repeat (x)
+          occ[j] = ex2_approx((K + (dd[j] + xa[j] + bn)) * kLog2e);
           if (!((okm >> j) & 1u)) occ[j] = 0.0f;
           // horizontal step re-emitting label[l-1] from the open state (classic_ctc_loss.py:617-626)
           const float dp = (j > 0) ? dd[j - 1] : d_left;

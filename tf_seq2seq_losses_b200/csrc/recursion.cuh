@@ -63,23 +63,32 @@ __device__ __forceinline__ void beta_step_simplified(float* bt, const float* d, 
   bt[NS - 1] = lse2(h + bt[NS - 1], d[NS - 1] + carry);
 }
 
+// The classic alpha step in two halves, so that a caller can hand S / x of the CURRENT frame to someone else before the
+// state moves on (the fused kernel publishes x and the open plane: they are all the occupancies of the frame need):
+//   prepare  S[l] = lse(A[l,0], A[l,1]),  x[l] = rep[l] ? A[l,0] : S[l]      (what a diagonal step out of state l carries)
+//   finish   A'[l,1] = lse(r[l] + A[l,1], d[l-1] + x[l-1]),  A'[l,0] = h + S[l]
 template <int NS>
-__device__ __forceinline__ void alpha_step_classic(float* a0, float* a1, const float* d, float h, int lane,
-                                                   const LabelBits<NS>& lb) {
+__device__ __forceinline__ void alpha_classic_prepare(const float* a0, const float* a1, const LabelBits<NS>& lb, float* S,
+                                                      float* x) {
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    S[j] = lse2(a0[j], a1[j]);
+    x[j] = ((lb.rep >> j) & 1u) ? a0[j] : S[j];
+  }
+}
+
+template <int NS>
+__device__ __forceinline__ void alpha_classic_finish(float* a0, float* a1, const float* S, const float* x, const float* d,
+                                                     float h, int lane, const LabelBits<NS>& lb) {
   // d of the left neighbour's top state: pure data, off the dependency chain
   float d_left = __shfl_up_sync(kFull, d[NS - 1], 1);
   if (lane == 0) d_left = kNegInf;
-  float S[NS];
-#pragma unroll
-  for (int j = NS - 1; j >= 0; --j) S[j] = lse2(a0[j], a1[j]);
-  const float x_top = ((lb.rep >> (NS - 1)) & 1u) ? a0[NS - 1] : S[NS - 1];
-  float x_left = __shfl_up_sync(kFull, x_top, 1);
+  float x_left = __shfl_up_sync(kFull, x[NS - 1], 1);
   if (lane == 0) x_left = kNegInf;
 #pragma unroll
   for (int j = NS - 1; j >= 1; --j) {
-    const float x = ((lb.rep >> (j - 1)) & 1u) ? a0[j - 1] : S[j - 1];
     const float r = ((lb.nb >> (j - 1)) & 1u) ? d[j - 1] : kNegInf;
-    a1[j] = lse2(r + a1[j], d[j - 1] + x);
+    a1[j] = lse2(r + a1[j], d[j - 1] + x[j - 1]);
   }
   {
     const float r = lb.nb_left ? d_left : kNegInf;
@@ -87,6 +96,14 @@ __device__ __forceinline__ void alpha_step_classic(float* a0, float* a1, const f
   }
 #pragma unroll
   for (int j = 0; j < NS; ++j) a0[j] = h + S[j];
+}
+
+template <int NS>
+__device__ __forceinline__ void alpha_step_classic(float* a0, float* a1, const float* d, float h, int lane,
+                                                   const LabelBits<NS>& lb) {
+  float S[NS], x[NS];
+  alpha_classic_prepare<NS>(a0, a1, lb, S, x);
+  alpha_classic_finish<NS>(a0, a1, S, x, d, h, lane, lb);
 }
 
 template <int NS>
