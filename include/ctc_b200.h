@@ -45,6 +45,10 @@ extern "C" {
 #define CTCB200_FORCE_FUSED 4u     /* ctcb200_loss_grad: use the fused kernel even for narrow vocabularies (V < 64), where the
                                       staged kernels are the default */
 
+#define CTCB200_TIME_MAJOR 8u      /* ctcb200_loss_grad only: logits and both gradient outputs are time-major, [T,B,V] (the layout
+                                      tf.nn.ctc_loss calls logits_time_major; the reference itself is batch-major only,
+                                      classic_ctc_loss.py:33-39).  Every other array keeps its layout. */
+
 /* Profiling aid: flags bits 8..15 select which stages of ctcb200_loss_grad are enqueued (bit 8+i = i-th name of
  * ctcb200_stage_names()); 0 = all.  A partial call must follow a full call on the same workspace and inputs. */
 #define CTCB200_STAGE_SHIFT 8

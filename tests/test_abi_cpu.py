@@ -84,6 +84,9 @@ def test_workspace_classes_and_kernel_choice():
     big_char = _lib.Desc(256, 255, 32, 255, 0, _lib.CLASSIC, 127, 0)         # the reference's tests/benchmark.py shape
     assert names(small_char).startswith("k1_") and names(big_char) == "kf_fused"
     assert names(_lib.Desc(32, 500, 29, 100, 0, _lib.CLASSIC, 101, _lib.FORCE_FUSED)) == "kf_fused"
+    time_major = _lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, _lib.TIME_MAJOR)
+    assert ws(time_major, _lib.WS_LOSS_GRAD_LOGITS) == ws(north_star, _lib.WS_LOSS_GRAD_LOGITS)      # scratch keeps its layout
+    assert ws(_lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, 16), _lib.WS_LOSS_GRAD) == 0     # unknown flag bit
     full_sweep = _lib.Desc(2048, 1600, 5000, 400, 0, _lib.CLASSIC, 401, 0)   # BASELINE configs[4] on one GPU
     assert names(full_sweep) == "kf_fused"
     assert ws(full_sweep, _lib.WS_LOSS_GRAD_LOGITS) + 2 * 2048 * 1600 * 5000 * 4 < 180e9      # fits one B200

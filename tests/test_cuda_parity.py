@@ -213,6 +213,39 @@ def test_narrow_vocabulary_large_batch_takes_the_fused_kernel(variant):
 
 
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_time_major_logits(variant, kernel_path):
+    """CTCB200_TIME_MAJOR / logits_time_major=True: logits and the gradient are [T,B,V]; same numbers as the batch-major
+    call on the transposed array (rows are processed identically, only their addresses change), ragged lengths, an
+    infeasible sample and an upstream gradient included."""
+    from tf_seq2seq_losses_b200 import _lib
+    for (B, T, V, L, seed) in [(5, 37, 96, 11, 8), (3, 20, 30, 6, 9)]:
+        logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
+        ll[0], tl[0] = L, L - 1                                  # infeasible: +inf, zero gradient rows
+        w = _cuda(np.linspace(0.5, 2.0, B).astype(np.float32))
+        outs = []
+        for time_major in (False, True):
+            x = _cuda(logits)
+            if time_major:
+                x = x.transpose(0, 1).contiguous()
+            x.requires_grad_(True)
+            loss = _fn(variant)(_cuda(labels), x, _cuda(ll), _cuda(tl), 0, logits_time_major=time_major)
+            (torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)) * w).sum().backward()
+            g = x.grad.transpose(0, 1) if time_major else x.grad
+            outs.append((loss.detach().cpu().numpy(), g.contiguous().cpu().numpy()))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.isinf(outs[0][0][0])
+        assert np.max(np.abs(outs[0][1] - outs[1][1])) <= 1e-6
+        assert np.array_equal(outs[1][1][0], np.zeros_like(outs[1][1][0]))
+        want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, variant, d_loss=w.cpu().numpy())
+        want_grad[np.isinf(want_loss)] = 0.0
+        assert np.max(np.abs(outs[1][1] - want_grad)) <= 2 * GRAD_ATOL_SHORT
+    # only the loss + gradient call takes the layout flag
+    x = _cuda(logits, torch.float32)
+    desc = _lib.make_desc(x.transpose(0, 1).contiguous(), _cuda(labels, torch.int32), 0, variant, L + 1, _lib.TIME_MAJOR)
+    with pytest.raises(_lib.CtcB200Error):
+        _lib.states(desc, x, _cuda(labels, torch.int32), _cuda(ll, torch.int32), _cuda(tl, torch.int32))
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
 def test_upstream_gradient_inside_the_kernels(variant, kernel_path):
     """ctcb200_loss_grad with a d_loss vector (forward_fn.backprop, base_loss.py:150-153, done inside the kernels: the
     scaled softmax pass and scatter of the fused kernel, the scale factor of K3), incl. negative, zero and unit weights."""

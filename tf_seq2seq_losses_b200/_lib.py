@@ -16,6 +16,7 @@ SIMPLIFIED = 1
 INPUT_LOGPROBAS = 1
 FORCE_STAGED = 2
 FORCE_FUSED = 4
+TIME_MAJOR = 8
 WS_LOSS_GRAD, WS_STATES, WS_HESSIAN, WS_LOSS_GRAD_LOGITS, WS_HVP_LOGITS = 0, 1, 2, 3, 4
 MAX_STATES = 512
 MAX_TOKENS = 32768
@@ -119,7 +120,10 @@ DEFAULT_FLAGS = FORCE_STAGED if os.environ.get("CTCB200_FORCE_STAGED", "0") == "
 
 
 def make_desc(logits: torch.Tensor, labels: torch.Tensor, blank: int, variant: int, U: int, flags: int = 0) -> Desc:
+    """Descriptor of a call on ``logits`` [B,T,V] (or [T,B,V] when ``flags`` has TIME_MAJOR)."""
     B, T, V = logits.shape
+    if int(flags) & TIME_MAJOR:
+        B, T = T, B
     return Desc(B, T, V, labels.shape[1], int(blank), int(variant), int(U), int(flags) | DEFAULT_FLAGS)
 
 

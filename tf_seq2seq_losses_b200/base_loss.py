@@ -223,6 +223,8 @@ class _FusedGradFn(torch.autograd.Function):
     def forward(ctx, logits, d_loss, grad, desc, aux):
         ctx.desc, ctx.aux = desc, aux
         ctx.save_for_backward(logits, d_loss, grad)
+        if desc.flags & _lib.TIME_MAJOR:
+            return d_loss[None, :, None] * grad
         return d_loss[:, None, None] * grad
 
     @staticmethod
@@ -230,26 +232,32 @@ class _FusedGradFn(torch.autograd.Function):
     def backward(ctx, v):
         logits, d_loss, grad = ctx.saved_tensors
         labels, label_length, logit_length = ctx.aux
+        time_major = bool(ctx.desc.flags & _lib.TIME_MAJOR)
+        if time_major and ctx.needs_input_grad[0]:
+            raise NotImplementedError("second derivative w.r.t. time-major logits: pass batch-major logits")
         d_logits = None
         if ctx.needs_input_grad[0]:
             # (d2 loss / d logits2) v = J^T H J v - s (p.v - p p^T v), J = I - 1 p^T per frame: one library call
             # (ctcb200_hvp_logits: K1, K2, K3, hvp_pre, K4<HVP>, hvp_post)
             d_logits = _lib.hvp_logits(ctx.desc, logits.detach().contiguous(), labels, label_length, logit_length, v,
                                        d_loss)
-        d_d_loss = (v * grad).sum(dim=(1, 2)) if ctx.needs_input_grad[1] else None
+        d_d_loss = (v * grad).sum(dim=(0, 2) if time_major else (1, 2)) if ctx.needs_input_grad[1] else None
         return d_logits, d_d_loss, None, None, None
 
 
 def ctc_loss(labels, logits, label_length, logit_length, blank_index, ctc_loss_data_cls,
-             max_label_length: Optional[int] = None) -> torch.Tensor:
-    """base_loss.py:38-68.  Returns the per-sample loss [B]; differentiable twice w.r.t. ``logits``."""
+             max_label_length: Optional[int] = None, logits_time_major: bool = False) -> torch.Tensor:
+    """base_loss.py:38-68.  Returns the per-sample loss [B]; differentiable twice w.r.t. ``logits``.
+    ``logits_time_major`` (keyword extension, the reference is batch-major only): ``logits`` is [T,B,V] and so is its
+    gradient; only the first derivative is available in that layout."""
     assert len(logits.shape) == 3
     assert logits.dtype == torch.float32
     labels_t, ll_t, tl_t = torch.as_tensor(labels), torch.as_tensor(label_length), torch.as_tensor(logit_length)
     assert len(labels_t.shape) == 2 and len(ll_t.shape) == 1 and len(tl_t.shape) == 1
-    assert logits.shape[0] == labels_t.shape[0] == ll_t.shape[0] == tl_t.shape[0]
+    assert logits.shape[1 if logits_time_major else 0] == labels_t.shape[0] == ll_t.shape[0] == tl_t.shape[0]
     dev = logits.device
     labels32, ll32, tl32 = _as_int32(labels_t, dev), _as_int32(ll_t, dev), _as_int32(tl_t, dev)
     U = _max_label_length_plus_one(ll_t, max_label_length)
-    desc = _lib.make_desc(logits, labels32, _blank_to_int(blank_index), ctc_loss_data_cls._variant, U, 0)
+    desc = _lib.make_desc(logits, labels32, _blank_to_int(blank_index), ctc_loss_data_cls._variant, U,
+                          _lib.TIME_MAJOR if logits_time_major else 0)
     return _FusedLossFn.apply(logits, labels32, ll32, tl32, desc)

@@ -20,7 +20,7 @@ class ClassicCtcLossData(BaseCtcLossData):
 
 def classic_ctc_loss(labels: torch.Tensor, logits: torch.Tensor, label_length: torch.Tensor,
                      logit_length: torch.Tensor, blank_index: Union[int, torch.Tensor] = 0,
-                     max_label_length: Optional[int] = None) -> torch.Tensor:
+                     max_label_length: Optional[int] = None, logits_time_major: bool = False) -> torch.Tensor:
     """Drop-in for classic_ctc_loss (classic_ctc_loss.py:33-70), same argument order and meaning as
     ``tf.nn.ctc_loss(..., logits_time_major=False)``.
 
@@ -31,9 +31,11 @@ def classic_ctc_loss(labels: torch.Tensor, logits: torch.Tensor, label_length: t
         logit_length:  int32   [batch]
         blank_index:   python int or scalar tensor
         max_label_length: optional keyword extension: max(label_length), to avoid reading it back from the device
+        logits_time_major: optional keyword extension (as in tf.nn.ctc_loss): logits are [max_length, batch, num_tokens]
 
     Returns: float32 [batch] per-sample loss (+inf where the label cannot be emitted); differentiable twice
     w.r.t. ``logits``.
     """
     return ctc_loss(labels=labels, logits=logits, label_length=label_length, logit_length=logit_length,
-                    blank_index=blank_index, ctc_loss_data_cls=ClassicCtcLossData, max_label_length=max_label_length)
+                    blank_index=blank_index, ctc_loss_data_cls=ClassicCtcLossData, max_label_length=max_label_length,
+                    logits_time_major=logits_time_major)

@@ -12,7 +12,8 @@ static int make_problem(const ctcb200_desc* d, Problem* p) {
   if (d->B < 0 || d->T < 0 || d->V < 1 || d->Lw < 0 || d->U < 0) return CTCB200_ERR_BAD_DESCRIPTOR;
   if (d->blank < 0 || d->blank >= d->V) return CTCB200_ERR_BAD_DESCRIPTOR;
   if (d->variant != CTCB200_CLASSIC && d->variant != CTCB200_SIMPLIFIED) return CTCB200_ERR_BAD_DESCRIPTOR;
-  if (d->flags & ~(CTCB200_INPUT_LOGPROBAS | CTCB200_FORCE_STAGED | CTCB200_FORCE_FUSED | CTCB200_STAGE_MASK))
+  if (d->flags & ~(CTCB200_INPUT_LOGPROBAS | CTCB200_FORCE_STAGED | CTCB200_FORCE_FUSED | CTCB200_TIME_MAJOR |
+                   CTCB200_STAGE_MASK))
     return CTCB200_ERR_BAD_DESCRIPTOR;
   p->B = d->B; p->T = d->T; p->V = d->V; p->Lw = d->Lw; p->blank = d->blank; p->variant = d->variant;
   p->U = d->U > 0 ? d->U : d->Lw + 1;
@@ -22,6 +23,9 @@ static int make_problem(const ctcb200_desc* d, Problem* p) {
   p->Upad = p->NS * kWarp;
   p->S = d->variant == CTCB200_CLASSIC ? 2 : 1;
   p->input_logprobas = (d->flags & CTCB200_INPUT_LOGPROBAS) != 0;
+  const bool tm = (d->flags & CTCB200_TIME_MAJOR) != 0;
+  p->stride_b = tm ? (size_t)d->V : (size_t)d->T * d->V;
+  p->stride_t = tm ? (size_t)d->B * d->V : (size_t)d->V;
   p->logits = nullptr; p->labels = nullptr; p->label_length = nullptr; p->logit_length = nullptr;
   return CTCB200_OK;
 }
@@ -184,6 +188,7 @@ int ctcb200_states(const ctcb200_desc* desc, const float* logits, const int32_t*
   int rc = check_common(desc, &p, CTCB200_WS_STATES, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, nullptr);
   if (rc != CTCB200_OK) return rc;
+  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (desc->U <= 0) return CTCB200_ERR_BAD_DESCRIPTOR;   // the output shape depends on the true U
   if (p.B == 0) return CTCB200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -199,6 +204,7 @@ int ctcb200_gamma(const ctcb200_desc* desc, const float* logits, const int32_t* 
   int rc = check_common(desc, &p, CTCB200_WS_STATES, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, nullptr);
   if (rc != CTCB200_OK) return rc;
+  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (desc->U <= 0) return CTCB200_ERR_BAD_DESCRIPTOR;   // the output shape depends on the true U
   if (p.NS > 4) return CTCB200_ERR_UNSUPPORTED_SIZE;
   if (p.B == 0) return CTCB200_OK;
@@ -216,6 +222,7 @@ int ctcb200_hessian(const ctcb200_desc* desc, const float* logits, const int32_t
   int rc = check_common(desc, &p, CTCB200_WS_HESSIAN, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, &gtmp);
   if (rc != CTCB200_OK) return rc;
+  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (p.B == 0 || p.T == 0) return CTCB200_OK;
   if (hessian == nullptr) return CTCB200_ERR_NULL_POINTER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -235,6 +242,7 @@ int ctcb200_hvp(const ctcb200_desc* desc, const float* logits, const int32_t* la
   int rc = check_common(desc, &p, CTCB200_WS_HESSIAN, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, &gtmp);
   if (rc != CTCB200_OK) return rc;
+  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (p.B == 0 || p.T == 0) return CTCB200_OK;
   if (d_gradient == nullptr || out == nullptr) return CTCB200_ERR_NULL_POINTER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -253,6 +261,7 @@ int ctcb200_hvp_logits(const ctcb200_desc* desc, const float* logits, const int3
   int rc = check_common(desc, &p, CTCB200_WS_HVP_LOGITS, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, &tmp);
   if (rc != CTCB200_OK) return rc;
+  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (p.B == 0 || p.T == 0) return CTCB200_OK;
   if (v == nullptr || out == nullptr) return CTCB200_ERR_NULL_POINTER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -86,6 +86,7 @@ struct Problem {
   int Upad;   // 32 * NS
   int S;      // 1 simplified, 2 classic (closed/open)
   bool input_logprobas;
+  size_t stride_b, stride_t;   // floats between consecutive utterances / frames of logits and gradients (see row_offset)
   const float* logits;
   const int32_t* labels;
   const int32_t* label_length;
@@ -106,6 +107,11 @@ struct Scratch {
   double* cb;      // [B*(T+1)]
   double* lossd;   // [B]
 };
+
+// offset of row (b, t) in logits / grad_logits / grad_logprobas: [B,T,V], or [T,B,V] with CTCB200_TIME_MAJOR
+__host__ __device__ __forceinline__ size_t row_offset(const Problem& p, int b, int t) {
+  return (size_t)b * p.stride_b + (size_t)t * p.stride_t;
+}
 
 // per-utterance clamped lengths
 __device__ __forceinline__ int utt_label_len(const Problem& p, int b) {

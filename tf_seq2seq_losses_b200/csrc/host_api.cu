@@ -37,6 +37,7 @@ void ctcb200_host_destroy(ctcb200_host_ctx* c) {
 int ctcb200_host_create(const ctcb200_desc* desc, int device, int num_slices, ctcb200_host_ctx** out) {
   if (desc == nullptr || out == nullptr) return CTCB200_ERR_NULL_POINTER;
   *out = nullptr;
+  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // batch slices must be contiguous
   if (num_slices < 1) num_slices = 1;
   if (desc->B > 0 && num_slices > desc->B) num_slices = desc->B;
   const int slice_b = desc->B > 0 ? (desc->B + num_slices - 1) / num_slices : 0;

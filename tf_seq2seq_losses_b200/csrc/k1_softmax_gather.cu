@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(kK1Warps * kWarp) k1_softmax_gather(Problem p,
   const int b = (int)(row / p.T), t = (int)(row % p.T);
   if (t >= utt_frames(p, b)) return;
   const int L = utt_label_len(p, b);
-  const float* x = p.logits + (size_t)row * p.V;
+  const float* x = p.logits + row_offset(p, b, t);
 
   float lse = 0.0f;
   if (!p.input_logprobas) {

@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(kK3Warps * kWarp)
 
   for (int t = t_begin + warp; t < t_end; t += kK3Warps) {
     const size_t row = (size_t)b * p.T + t;
-    float* gl = grad_logits ? grad_logits + row * p.V : nullptr;
-    float* gp = grad_logprobas ? grad_logprobas + row * p.V : nullptr;
+    float* gl = grad_logits ? grad_logits + row_offset(p, b, t) : nullptr;
+    float* gp = grad_logprobas ? grad_logprobas + row_offset(p, b, t) : nullptr;
     if (dead || t >= n_t) {          // frames beyond logit_length and infeasible samples: exact zeros
       zero_row(gl, p.V, lane);
       zero_row(gp, p.V, lane);
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kK3Warps * kWarp)
                                                          map, acc);
 
     // dense row
-    const float* x = p.logits + row * p.V;
+    const float* x = p.logits + row_offset(p, b, t);
     const float lse_row = s.rowlse[row];
     const float scale = dl * occ_sum;
     const bool vec = ((p.V & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&

@@ -393,7 +393,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   const int n_my = (count > w) ? (count - w + W - 1) / W : 0;
   const unsigned row_bytes = (unsigned)V * 4u;
   constexpr bool tma = TMA;
-  const float* logits_b = p.logits + (size_t)b * p.T * V;
+  const float* logits_b = p.logits + row_offset(p, b, 0);
   float* rowbuf = sv.row + (size_t)w * f.SL * Vp;
   float* rowx = sv.aux_rows + (size_t)w * Vp;
   auto slot_ptr = [&](int q) { return (q < f.SL) ? rowbuf + (size_t)q * Vp : rowx; };
@@ -401,7 +401,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   // (one elected lane) or, when rows are not 16-byte aligned, by every lane's cp.async completion.
   auto load_row = [&](int q, int t) {
     float* dst = slot_ptr(q);
-    const float* src = logits_b + (size_t)t * V;
+    const float* src = logits_b + (size_t)t * p.stride_t;
     if (tma) {
       if (lane == 0) {
         fence_proxy_async();
@@ -666,7 +666,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       const float occ_blank = 1.0f - warp_sum(osum);
       if (lane == 0) row[p.blank] -= dl * occ_blank;
       __syncwarp();
-      float* gdst = a.grad + ((size_t)b * p.T + t) * V;
+      float* gdst = a.grad + row_offset(p, b, t);
       if (tma) {
         if (lane == 0) {
           fence_proxy_async();                                  // generic-proxy writes -> visible to the TMA store
@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
   }
   if (role > 0) {     // frames beyond logit_length, or every frame of an infeasible sample: exact zeros
     const int widx = side * W + (role - 1);
-    for (int r = (dead ? 0 : n_t) + widx; r < p.T; r += 2 * W) fused_zero_row(a.grad + ((size_t)b * p.T + r) * p.V, p.V, lane, TMA);
+    for (int r = (dead ? 0 : n_t) + widx; r < p.T; r += 2 * W) fused_zero_row(a.grad + row_offset(p, b, r), p.V, lane, TMA);
   }
 }
 
