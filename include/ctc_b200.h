@@ -72,6 +72,7 @@ extern "C" {
  * otherwise the two are equal.  A workspace sized with CTCB200_WS_LOSS_GRAD is always accepted as well. */
 #define CTCB200_WS_LOSS_GRAD_LOGITS 3
 #define CTCB200_WS_HVP_LOGITS 4       /* ctcb200_hvp_logits */
+#define CTCB200_WS_DECODE 5           /* ctcb200_greedy_decode */
 
 typedef struct ctcb200_desc {
   int32_t B;       /* batch size                      (>= 0) */
@@ -155,6 +156,17 @@ int ctcb200_hvp(const ctcb200_desc* desc, const float* logits, const int32_t* la
 int ctcb200_hvp_logits(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
                        const int32_t* label_length, const int32_t* logit_length, const float* d_loss, const float* v,
                        float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Greedy (best-path) decoding of the same logits, the inference-time step after the loss: per frame t < logit_length the
+ * arg-max token (lowest index on ties), repeats merged when merge_repeated != 0, blanks dropped -- what
+ * tf.nn.ctc_greedy_decoder returns for the logits classic_ctc_loss (classic_ctc_loss.py:33-70) is trained on, in dense
+ * form: decoded [B,T] int32 padded with -1, decoded_length [B], neg_sum_logits [B] = -sum_t max_k logits (may be NULL).
+ * desc->Lw, U and variant are ignored; CTCB200_TIME_MAJOR is honoured; workspace sized with CTCB200_WS_DECODE.
+ */
+int ctcb200_greedy_decode(const ctcb200_desc* desc, const float* logits, const int32_t* logit_length, int merge_repeated,
+                          int32_t* decoded, int32_t* decoded_length, float* neg_sum_logits, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /*
  * Host-buffer convenience path (what a framework without device tensors, or the end-to-end benchmark, calls):

@@ -540,3 +540,28 @@ def hessian_logits(data: CtcLossData, logprobas: np.ndarray, hessian: np.ndarray
         blk = np.einsum("bi,ij->bij", p[:, t], np.eye(V)) - p[:, t, :, None] * p[:, t, None, :]
         out[:, t, :, t, :] -= s[:, t, None, None] * blk
     return out
+
+
+def greedy_decode(logits: np.ndarray, logit_length, blank_index: int = 0, merge_repeated: bool = True):
+    """Best-path decoding as tf.nn.ctc_greedy_decoder defines it (not part of tf_seq2seq_losses; checker for
+    ctcb200_greedy_decode): per frame t < logit_length the arg-max token (np.argmax: lowest index on ties), repeats merged,
+    blanks dropped.  Returns (decoded [B,T] int32 padded with -1, decoded_length [B], neg_sum_logits [B])."""
+    logits = np.asarray(logits)
+    B, T, _ = logits.shape
+    decoded = np.full((B, T), -1, dtype=np.int32)
+    length = np.zeros((B,), dtype=np.int32)
+    neg_sum = np.zeros((B,), dtype=np.float64)
+    for b in range(B):
+        n = max(0, min(int(logit_length[b]), T))
+        best = np.argmax(logits[b, :n], axis=1) if n else np.zeros((0,), dtype=np.int64)
+        neg_sum[b] = -float(np.sum(np.max(logits[b, :n].astype(np.float64), axis=1))) if n else 0.0
+        k, prev = 0, -1
+        for t in range(n):
+            tok = int(best[t])
+            if tok != blank_index and not (merge_repeated and tok == prev):
+                decoded[b, k] = tok
+                k += 1
+            prev = tok
+        length[b] = k
+    return decoded, length, neg_sum
+

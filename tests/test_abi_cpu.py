@@ -76,7 +76,8 @@ def test_workspace_classes_and_kernel_choice():
     assert names(north_star) == "kf_fused" and lib.ctcb200_launches_per_call(ctypes.byref(north_star)) == 1
     assert ws(north_star, _lib.WS_LOSS_GRAD_LOGITS) * 2 < ws(north_star, _lib.WS_LOSS_GRAD)
     assert ws(north_star, _lib.WS_HVP_LOGITS) > ws(north_star, _lib.WS_HESSIAN) > ws(north_star, _lib.WS_STATES)
-    assert ws(north_star, 5) == 0 and ws(north_star, -1) == 0
+    assert ws(north_star, _lib.WS_DECODE) == 2 * 256 * 1000 * 4          # arg-max token + its logit per row
+    assert ws(north_star, 6) == 0 and ws(north_star, -1) == 0
     staged = _lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, _lib.FORCE_STAGED)
     assert names(staged) == "k1_softmax_gather,k2_recursion,k3_grad"
     assert ws(staged, _lib.WS_LOSS_GRAD_LOGITS) == ws(staged, _lib.WS_LOSS_GRAD)

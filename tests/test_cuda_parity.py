@@ -566,6 +566,30 @@ def test_config4_full_batch_on_one_gpu():
     assert err <= GRAD_ATOL_LONG
 
 
+@pytest.mark.parametrize("merge_repeated", [True, False])
+def test_greedy_decode_matches_oracle(merge_repeated):
+    """ctcb200_greedy_decode (tf.nn.ctc_greedy_decoder in dense form) is integer work: bit-exact against the oracle, with
+    ties (integer-valued logits: lowest index wins), ragged and zero lengths, a non-zero blank, unaligned rows, and the
+    time-major layout."""
+    pkg = _pkg()
+    rng = np.random.default_rng(17)
+    for (B, T, V, blank, ties) in [(5, 40, 29, 0, False), (4, 33, 64, 7, True), (3, 70, 1024, 1023, False), (2, 9, 4, 2, True)]:
+        logits = rng.standard_normal((B, T, V)).astype(np.float32)
+        if ties:
+            logits = np.round(logits * 1.5).astype(np.float32)
+        tl = rng.integers(0, T + 1, size=B).astype(np.int32)
+        tl[0] = T
+        want_dec, want_len, want_neg = orc.greedy_decode(logits, tl, blank, merge_repeated)
+        for time_major in (False, True):
+            x = _cuda(logits)
+            if time_major:
+                x = x.transpose(0, 1).contiguous()
+            dec, length, neg = pkg.ctc_greedy_decode(x, _cuda(tl), blank, merge_repeated, time_major=time_major)
+            assert np.array_equal(dec.cpu().numpy(), want_dec)
+            assert np.array_equal(length.cpu().numpy(), want_len)
+            assert np.allclose(neg.cpu().numpy(), want_neg, rtol=1e-5, atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # boundary behaviour
 # ------------------------------------------------------------------------------------------------------------------

@@ -196,3 +196,21 @@ def test_degenerate_shapes(variant):
     # label_length == 0: loss = -sum_t h[t]
     loss, grad, _ = orc.loss_and_grad_logits(np.array([[1, 2]]), np.zeros((1, 3, 3)), np.array([0]), np.array([3]), 0, variant)
     assert abs(loss[0] - 3 * np.log(3)) < 1e-12
+
+
+def test_greedy_decode_known_answers():
+    """Hand-checked best-path decodings (collapse repeats, then drop blanks -- "a_bb_ccc_c -> abcc", README.md:31 of the
+    reference describes the same collapsing rule for the classic loss)."""
+    path = [1, 0, 2, 2, 0, 3, 3, 3, 0, 3]                       # a _ b b _ c c c _ c  with blank 0
+    logits = np.full((1, len(path), 4), -1.0, dtype=np.float32)
+    logits[0, np.arange(len(path)), path] = 2.0
+    dec, length, neg = orc.greedy_decode(logits, [len(path)], 0, True)
+    assert dec[0, :4].tolist() == [1, 2, 3, 3] and length.tolist() == [4] and (dec[0, 4:] == -1).all()
+    assert abs(neg[0] + 2.0 * len(path)) < 1e-12
+    dec, length, _ = orc.greedy_decode(logits, [len(path)], 0, False)
+    assert dec[0, :7].tolist() == [1, 2, 2, 3, 3, 3, 3] and length.tolist() == [7]
+    dec, length, _ = orc.greedy_decode(logits, [3], 0, True)     # only the first three frames count
+    assert dec[0, :2].tolist() == [1, 2] and length.tolist() == [2]
+    dec, length, _ = orc.greedy_decode(np.zeros((1, 3, 4), dtype=np.float32), [3], 0, True)   # ties: index 0 = blank
+    assert length.tolist() == [0]
+

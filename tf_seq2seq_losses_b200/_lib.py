@@ -17,7 +17,7 @@ INPUT_LOGPROBAS = 1
 FORCE_STAGED = 2
 FORCE_FUSED = 4
 TIME_MAJOR = 8
-WS_LOSS_GRAD, WS_STATES, WS_HESSIAN, WS_LOSS_GRAD_LOGITS, WS_HVP_LOGITS = 0, 1, 2, 3, 4
+WS_LOSS_GRAD, WS_STATES, WS_HESSIAN, WS_LOSS_GRAD_LOGITS, WS_HVP_LOGITS, WS_DECODE = 0, 1, 2, 3, 4, 5
 MAX_STATES = 512
 MAX_TOKENS = 32768
 
@@ -27,7 +27,7 @@ _LIB_PATH = os.environ.get("CTCB200_LIB", os.path.join(os.path.dirname(os.path.a
 EXPORTED_SYMBOLS = (
     "ctcb200_version", "ctcb200_strerror", "ctcb200_stage_names", "ctcb200_launches_per_call",
     "ctcb200_workspace_bytes", "ctcb200_loss_grad", "ctcb200_states",
-    "ctcb200_hessian", "ctcb200_hvp", "ctcb200_hvp_logits", "ctcb200_gamma", "ctcb200_host_create", "ctcb200_host_loss_grad",
+    "ctcb200_hessian", "ctcb200_hvp", "ctcb200_hvp_logits", "ctcb200_gamma", "ctcb200_greedy_decode", "ctcb200_host_create", "ctcb200_host_loss_grad",
     "ctcb200_host_grad_device_ptr", "ctcb200_host_destroy",
 )
 
@@ -79,6 +79,8 @@ def load() -> ctypes.CDLL:
     lib.ctcb200_hvp.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, vp, ctypes.c_size_t, vp]
     lib.ctcb200_hvp_logits.restype = ctypes.c_int
     lib.ctcb200_hvp_logits.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, fp, vp, ctypes.c_size_t, vp]
+    lib.ctcb200_greedy_decode.restype = ctypes.c_int
+    lib.ctcb200_greedy_decode.argtypes = [dp, fp, i32p, ctypes.c_int, i32p, i32p, fp, vp, ctypes.c_size_t, vp]
     lib.ctcb200_host_create.restype = ctypes.c_int
     lib.ctcb200_host_create.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
     lib.ctcb200_host_loss_grad.restype = ctypes.c_int
@@ -226,6 +228,27 @@ def hvp_logits(desc: Desc, logits, labels, label_length, logit_length, v, d_loss
                                             _ptr(logit_length), _ptr(d_loss), _ptr(v), _ptr(out), _ptr(ws), ws.numel(),
                                             _stream(dev)))
     return out
+
+
+def greedy_decode(logits, logit_length, blank: int = 0, merge_repeated: bool = True, time_major: bool = False):
+    """ctcb200_greedy_decode.  Returns (decoded [B,T] int32 padded with -1, decoded_length [B], neg_sum_logits [B])."""
+    _require_cuda(logits, "logits")
+    dev = logits.device
+    x = logits.detach().contiguous()
+    B, T, V = x.shape
+    if time_major:
+        B, T = T, B
+    desc = Desc(B, T, V, 0, int(blank), CLASSIC, 1, TIME_MAJOR if time_major else 0)
+    tl = logit_length.to(device=dev, dtype=torch.int32).contiguous()
+    decoded = torch.empty((B, T), dtype=torch.int32, device=dev)
+    length = torch.empty((B,), dtype=torch.int32, device=dev)
+    neg_sum = torch.empty((B,), dtype=torch.float32, device=dev)
+    ws = _workspace(desc, WS_DECODE, dev)
+    if B > 0:
+        with torch.cuda.device(dev):
+            check(load().ctcb200_greedy_decode(ctypes.byref(desc), _ptr(x), _ptr(tl), int(bool(merge_repeated)), _ptr(decoded),
+                                               _ptr(length), _ptr(neg_sum), _ptr(ws), ws.numel(), _stream(dev)))
+    return decoded, length, neg_sum
 
 
 class HostContext:

@@ -39,6 +39,12 @@ struct Carve {
 // offset vector; the gathered rows, the second state tensor and its offsets (staged kernels) are left out.
 static size_t carve(const Problem& p, int what, bool fused_only, char* base, Scratch* s, float** grad_tmp) {
   Carve c;
+  if (what == CTCB200_WS_DECODE) {       // arg-max token and its logit per row; nothing else
+    const size_t o = c.take((size_t)p.B * p.T * 4);
+    c.take((size_t)p.B * p.T * 4);
+    if (base != nullptr && grad_tmp != nullptr) *grad_tmp = reinterpret_cast<float*>(base + o);
+    return c.off;
+  }
 #ifdef CTCB200_FUSED_TIMING
   const bool staged = true;            // the instrumented kernel writes its counters into the (otherwise unused) beta scratch
   (void)fused_only;
@@ -152,7 +158,7 @@ int ctcb200_launches_per_call(const ctcb200_desc* desc) {
 size_t ctcb200_workspace_bytes(const ctcb200_desc* desc, int what) {
   Problem p;
   if (make_problem(desc, &p) != CTCB200_OK) return 0;
-  if (what < CTCB200_WS_LOSS_GRAD || what > CTCB200_WS_HVP_LOGITS) return 0;
+  if (what < CTCB200_WS_LOSS_GRAD || what > CTCB200_WS_DECODE) return 0;
   return carve(p, what, fused_only_ws(desc, p, what), nullptr, nullptr, nullptr);
 }
 
@@ -273,6 +279,22 @@ int ctcb200_hvp_logits(const ctcb200_desc* desc, const float* logits, const int3
   CTCB200_CUDA(launch_hvp_pre(p, s, v, w, pv, st));
   CTCB200_CUDA(launch_hessian(p, s, g, nullptr, w, y, st));
   CTCB200_CUDA(launch_hvp_post(p, s, v, y, g, pv, d_loss, out, st));
+  return CTCB200_OK;
+}
+
+int ctcb200_greedy_decode(const ctcb200_desc* desc, const float* logits, const int32_t* logit_length, int merge_repeated,
+                          int32_t* decoded, int32_t* decoded_length, float* neg_sum_logits, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  Problem p; Scratch s; float* tmp = nullptr;
+  // labels / label_length play no part in decoding: the logit lengths stand in for them in the common pointer checks
+  int rc = check_common(desc, &p, CTCB200_WS_DECODE, logits, logit_length, logit_length, logit_length, workspace,
+                        workspace_bytes, &s, &tmp);
+  if (rc != CTCB200_OK) return rc;
+  if (p.B == 0) return CTCB200_OK;
+  if (decoded == nullptr || decoded_length == nullptr) return CTCB200_ERR_NULL_POINTER;
+  const size_t n = align256((size_t)p.B * p.T * 4) / 4;
+  CTCB200_CUDA(launch_greedy_decode(p, reinterpret_cast<int*>(tmp), tmp + n, merge_repeated, decoded, decoded_length,
+                                    neg_sum_logits, static_cast<cudaStream_t>(stream)));
   return CTCB200_OK;
 }
 

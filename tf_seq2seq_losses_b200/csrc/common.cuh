@@ -136,6 +136,8 @@ cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss
                          cudaStream_t st);
 cudaError_t launch_export_states(const Problem& p, const Scratch& s, float* alpha, float* beta, cudaStream_t st);
 cudaError_t launch_gamma(const Problem& p, const Scratch& s, float* gamma, cudaStream_t st);
+cudaError_t launch_greedy_decode(const Problem& p, int* best, float* bestv, int merge_repeated, int* decoded,
+                                 int* decoded_length, float* neg_sum_logits, cudaStream_t st);
 cudaError_t launch_hvp_pre(const Problem& p, const Scratch& s, const float* v, float* w, float* pv, cudaStream_t st);
 cudaError_t launch_hvp_post(const Problem& p, const Scratch& s, const float* v, const float* y, const float* g,
                             const float* pv, const float* d_loss, float* out, cudaStream_t st);
