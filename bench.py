@@ -133,7 +133,7 @@ def cpu_port_samples_per_s(variant_id, logits, labels, label_length, logit_lengt
     return x.shape[0] / dt, dt, c_oracle.max_threads()
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """--impl reference: the reference's algorithm on the host cores (oracle port; TensorFlow is not installable
     here, so the reference itself cannot run).  Rank 0 only."""
     if rank != 0:
@@ -165,16 +165,26 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    }), file=out, flush=True)
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner on communicator
+    creation): from here on file descriptor 1 points at stderr and the returned handle is the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
     args = parse_args()
+    out = claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch
@@ -186,8 +196,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     B, T, V, L, dvar = WORKLOADS[args.workload]
@@ -340,7 +348,7 @@ def main():
                        "l2": "inputs exceed L2 (logits+grad per step >> 126 MB), no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
-        }), flush=True)
+        }), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
