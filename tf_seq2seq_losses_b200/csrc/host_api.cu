@@ -1,6 +1,7 @@
 // Host-buffer entry points of libctc_b200.so (include/ctc_b200.h): the call a host without device tensors makes.
-// The batch is cut into slices; slice i's host->device copies, kernels and device->host copies are enqueued on
-// stream i % 2, so the PCIe copies of one slice overlap the kernels of the other.
+// The batch is cut into slices.  All host->device copies go back to back on one copy stream (the PCIe link never idles
+// between slices); each slice's kernels and its loss read-back run on a second stream as soon as that slice's event
+// fires, so everything but the last slice's kernel hides under the copies.
 #include <new>
 
 #include "common.cuh"
@@ -9,7 +10,8 @@ struct ctcb200_host_ctx {
   ctcb200_desc desc;
   int device;
   int num_slices;
-  cudaStream_t streams[2];
+  cudaStream_t streams[2];      // [0] copies host -> device, [1] kernels and device -> host
+  cudaEvent_t* landed;          // [num_slices] slice i is on the device
   float* d_logits;
   float* d_grad;
   int32_t* d_labels;
@@ -28,6 +30,11 @@ void ctcb200_host_destroy(ctcb200_host_ctx* c) {
   for (int i = 0; i < 2; ++i) {
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->ws[i]) cudaFree(c->ws[i]);
+  }
+  if (c->landed) {
+    for (int i = 0; i < c->num_slices; ++i)
+      if (c->landed[i]) cudaEventDestroy(c->landed[i]);
+    delete[] c->landed;
   }
   cudaFree(c->d_logits); cudaFree(c->d_grad); cudaFree(c->d_labels); cudaFree(c->d_label_length);
   cudaFree(c->d_logit_length); cudaFree(c->d_loss);
@@ -50,10 +57,11 @@ int ctcb200_host_create(const ctcb200_desc* desc, int device, int num_slices, ct
   c->desc = *desc; c->device = device; c->num_slices = num_slices; c->ws_bytes = ws_bytes;
   const size_t n = (size_t)desc->B * desc->T * desc->V;
   bool ok = cudaSetDevice(device) == cudaSuccess;
-  for (int i = 0; i < 2 && ok; ++i) {
-    ok = ok && cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->ws[i], ws_bytes ? ws_bytes : 256) == cudaSuccess;
-  }
+  for (int i = 0; i < 2 && ok; ++i) ok = ok && cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->ws[0], ws_bytes ? ws_bytes : 256) == cudaSuccess;     // kernels run in order: one workspace
+  c->landed = new (std::nothrow) cudaEvent_t[num_slices]();
+  ok = ok && c->landed != nullptr;
+  for (int i = 0; i < num_slices && ok; ++i) ok = ok && cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_logits, n ? n * 4 : 256) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_grad, n ? n * 4 : 256) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_labels, (size_t)desc->B * desc->Lw * 4 + 256) == cudaSuccess;
@@ -84,24 +92,26 @@ int ctcb200_host_loss_grad(ctcb200_host_ctx* c, const float* host_logits, const 
   const int slice_b = (d.B + c->num_slices - 1) / c->num_slices;
   const size_t tv = (size_t)d.T * d.V;
   int rc = CTCB200_OK;
+  cudaStream_t copy = c->streams[0], run = c->streams[1];
   for (int i = 0, b0 = 0; b0 < d.B; ++i, b0 += slice_b) {
     const int nb = (d.B - b0 < slice_b) ? d.B - b0 : slice_b;
-    cudaStream_t st = c->streams[i & 1];
     ctcb200_desc sd = d;
     sd.B = nb;
     bool ok = true;
-    if (tv) ok = ok && cudaMemcpyAsync(c->d_logits + b0 * tv, host_logits + b0 * tv, nb * tv * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    if (d.Lw) ok = ok && cudaMemcpyAsync(c->d_labels + (size_t)b0 * d.Lw, host_labels + (size_t)b0 * d.Lw, (size_t)nb * d.Lw * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(c->d_label_length + b0, host_label_length + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(c->d_logit_length + b0, host_logit_length + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (tv) ok = ok && cudaMemcpyAsync(c->d_logits + b0 * tv, host_logits + b0 * tv, nb * tv * 4, cudaMemcpyHostToDevice, copy) == cudaSuccess;
+    if (d.Lw) ok = ok && cudaMemcpyAsync(c->d_labels + (size_t)b0 * d.Lw, host_labels + (size_t)b0 * d.Lw, (size_t)nb * d.Lw * 4, cudaMemcpyHostToDevice, copy) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->d_label_length + b0, host_label_length + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, copy) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->d_logit_length + b0, host_logit_length + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, copy) == cudaSuccess;
+    ok = ok && cudaEventRecord(c->landed[i], copy) == cudaSuccess;
+    ok = ok && cudaStreamWaitEvent(run, c->landed[i], 0) == cudaSuccess;
     if (!ok) { rc = CTCB200_ERR_CUDA; break; }
     rc = ctcb200_loss_grad(&sd, c->d_logits + b0 * tv, c->d_labels + (size_t)b0 * d.Lw, c->d_label_length + b0,
                            c->d_logit_length + b0, nullptr, c->d_loss + b0, c->d_grad + b0 * tv, nullptr,
-                           c->ws[i & 1], c->ws_bytes, st);
+                           c->ws[0], c->ws_bytes, run);
     if (rc != CTCB200_OK) break;
-    ok = cudaMemcpyAsync(host_loss + b0, c->d_loss + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok = cudaMemcpyAsync(host_loss + b0, c->d_loss + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, run) == cudaSuccess;
     if (host_grad_logits && tv)
-      ok = ok && cudaMemcpyAsync(host_grad_logits + b0 * tv, c->d_grad + b0 * tv, nb * tv * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+      ok = ok && cudaMemcpyAsync(host_grad_logits + b0 * tv, c->d_grad + b0 * tv, nb * tv * 4, cudaMemcpyDeviceToHost, run) == cudaSuccess;
     if (!ok) { rc = CTCB200_ERR_CUDA; break; }
   }
   for (int i = 0; i < 2; ++i)
