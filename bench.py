@@ -325,7 +325,7 @@ def main():
         e2e = {"value": global_B / float(tt.item()), "unit": "samples/s",
                "h2d_bytes_per_step": int(sum(p.numel() * p.element_size() for p in pin)),
                "d2h_bytes_per_step": int(loss_pin.numel() * 4), "ms_per_step": float(tt.item()) * 1e3,
-               "steps": args.e2e_steps, "api": "ctcb200_host_loss_grad (pinned host buffers, 8 slices on 2 streams)"}
+               "steps": args.e2e_steps, "api": "ctcb200_host_loss_grad (pinned host buffers, 8 slices, copy stream + compute stream)"}
         assert torch.equal(loss_pin, loss.cpu()), "host entry point disagrees with the device entry point"
         ctx.close()
 
