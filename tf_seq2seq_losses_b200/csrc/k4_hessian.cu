@@ -266,17 +266,15 @@ template <int NS, bool CLASSIC>
 __device__ __forceinline__ void subtract_frame_occupancies(const float* a0, const float* a1, const float* b0,
                                                            const float* b1, const float* dd, float h, float K,
                                                            const int* tok, int tok_left, int blank, int V, int lane,
-                                                           float* row) {
+                                                           float* row, float total) {
   constexpr float kLog2e = 1.4426950408889634f;
-  float occ[NS], occ_stay[NS], x[NS];
-  float xm = kNegInf;
+  float occ[NS], occ_stay[NS];
+  (void)h;
   if (!CLASSIC) {
     float bx = __shfl_down_sync(kFull, b0[0], 1);
     if (lane == 31) bx = kNegInf;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-      x[j] = a0[j] + b0[j];
-      xm = fmaxf(xm, x[j]);
       const float bn = (j < NS - 1) ? b0[j + 1] : bx;
       occ[j] = ex2_approx((K + (a0[j] + dd[j] + bn)) * kLog2e);
       if (!((tok[j] != blank) && (tok[j] >= 0) && (tok[j] < V))) occ[j] = 0.0f;
@@ -290,8 +288,6 @@ __device__ __forceinline__ void subtract_frame_occupancies(const float* a0, cons
     for (int j = 0; j < NS; ++j) {
       const int tp = (j > 0) ? tok[j - 1] : tok_left;
       const float sj = lse2(a0[j], a1[j]);
-      x[j] = sj + b0[j];
-      xm = fmaxf(xm, x[j]);
       const float bn = (j < NS - 1) ? b1[j + 1] : bx;
       occ[j] = ex2_approx((K + (dd[j] + ((tok[j] == tp) ? a0[j] : sj) + bn)) * kLog2e);
       if (!((tok[j] != blank) && (tok[j] >= 0) && (tok[j] < V))) occ[j] = 0.0f;
@@ -304,17 +300,18 @@ __device__ __forceinline__ void subtract_frame_occupancies(const float* a0, cons
 #pragma unroll
     for (int j = 0; j < NS; ++j) occ[j] += (j < NS - 1) ? occ_stay[j + 1] : s_next;
   }
+  // The conditioned chain carries the probability mass `total` (= the occupancy of the conditioning emission, -g[t,k]) and
+  // every alignment emits exactly one symbol per frame, so the blank's joint occupancy is `total` minus the others: one
+  // warp sum instead of the log-sum-exp over states the reference forms (classic_ctc_loss.py:608-614,
+  // simplified_ctc_loss.py:498-501).  Measured 6-7 % faster on the dense Hessian and on the HVP.
+  float osum = 0.0f;
 #pragma unroll
-  for (int j = 0; j < NS; ++j)
+  for (int j = 0; j < NS; ++j) {
+    osum += occ[j];
     if (occ[j] > 0.0f) atomicAdd(&row[tok[j]], -occ[j]);
-  const float XM = warp_max(xm);
-  const float XM0 = (XM == kNegInf) ? 0.0f : XM;
-  float xs = 0.0f;
-#pragma unroll
-  for (int j = 0; j < NS; ++j) xs += ex2_approx((x[j] - XM0) * kLog2e);
-  xs = warp_sum(xs);
-  const float occ_blank = (XM == kNegInf) ? 0.0f : __expf(K + (h + (XM + __logf(xs))));
-  if (lane == 0) atomicAdd(&row[blank], -occ_blank);
+  }
+  osum = warp_sum(osum);
+  if (lane == 0) atomicAdd(&row[blank], -(total - osum));
 }
 
 template <int NS>
@@ -441,7 +438,7 @@ __global__ void __launch_bounds__(kK4Warps * kWarp)
       for (int k2 = lane; k2 < p.V; k2 += kWarp) row[k2] = gk * g2[k2];
       __syncwarp();
       const float K = (float)(lossd + ca_b[t] + cb_b[t2 + 1]);
-      subtract_frame_occupancies<NS, CLASSIC>(v0, v1, bn0, bn1, d2, h2, K, tok, tok_left, p.blank, p.V, lane, row);
+      subtract_frame_occupancies<NS, CLASSIC>(v0, v1, bn0, bn1, d2, h2, K, tok, tok_left, p.blank, p.V, lane, row, -gk);
       finish_row(t2, hv, hk);
       if (CLASSIC) alpha_step_classic<NS>(v0, v1, d2, h2, lane, lb);
       else alpha_step_simplified<NS>(v0, d2, h2, lane);
@@ -484,7 +481,7 @@ __global__ void __launch_bounds__(kK4Warps * kWarp)
       for (int k2 = lane; k2 < p.V; k2 += kWarp) row[k2] = gk * g2[k2];
       __syncwarp();
       const float K = (float)(lossd + ca_b[t2] + cb_b[t + 1]);
-      subtract_frame_occupancies<NS, CLASSIC>(al0, al1, v0, v1, d2, h2, K, tok, tok_left, p.blank, p.V, lane, row);
+      subtract_frame_occupancies<NS, CLASSIC>(al0, al1, v0, v1, d2, h2, K, tok, tok_left, p.blank, p.V, lane, row, -gk);
       finish_row(t2, hv, hk);
       if (CLASSIC) beta_step_classic<NS>(v0, v1, d2, h2, lane, lb);
       else beta_step_simplified<NS>(v0, d2, h2, lane);
