@@ -93,6 +93,25 @@ def test_workspace_classes_and_kernel_choice():
     assert ws(full_sweep, _lib.WS_LOSS_GRAD_LOGITS) + 2 * 2048 * 1600 * 5000 * 4 < 180e9      # fits one B200
 
 
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/ctc_b200.h is the whole contract: it compiles as C99 with -pedantic (no CUDA, torch or C++ in the
+    signatures) and a C program linked against libctc_b200.so calls the sizing / diagnostic entry points."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = os.path.join(ROOT, "tests", "abi_smoke.c")
+    libdir = os.path.join(ROOT, "tf_seq2seq_losses_b200")
+    _lib.load()                                                # raises when the library has not been built
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                    "-I", os.path.join(ROOT, "include"), src], check=True)
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir,
+                    "-l:libctc_b200.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == 232682496 and int(out[1]) > int(out[0])     # 0.23 GB of scratch for the north-star call
+
+
 def test_python_face_has_no_cpu_fallback():
     import tf_seq2seq_losses_b200 as pkg
     logits = torch.zeros((1, 4, 3))
