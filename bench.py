@@ -2,7 +2,7 @@
 """Benchmark of the CTC loss+gradient hot path (BASELINE.json metric) on 1..8 B200.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4]
-                  [--variant simplified|classic] [--scaling weak|strong] [--ragged]
+                  [--variant simplified|classic] [--scaling strong|weak] [--ragged] [--e2e-grad]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one fused loss + d/dlogits call over one synthetic batch (logits ~ N(0,1), labels ~ U{1..V-1}).
@@ -42,11 +42,14 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default=None, choices=["simplified", "classic"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default): the named batch is cut into N contiguous slices, one per GPU (SURVEY.md 8e); "
+                         "weak: every GPU processes the whole named batch.  The other one is reported under 'secondary'.")
     ap.add_argument("--staged", action="store_true", help="force the three staged kernels instead of the fused one")
     ap.add_argument("--ragged", action="store_true", help="logit_length~U[T/2,T], label_length~U[L/2,L]")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other scaling mode's measurement at N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=64, help="utterances timed by the CPU baseline leg")
     return ap.parse_args()
@@ -168,6 +171,23 @@ def run_reference(args, rank, world, out):
     }), file=out, flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Best effort: run this rank's host threads (and so its first-touch pinned allocations) on the CPUs NVML lists as
+    local to the GPU.  On boxes where every GPU reports the same node this is a no-op."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def claim_stdout():
     """stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner on communicator
     creation): from here on file descriptor 1 points at stderr and the returned handle is the real stdout."""
@@ -282,7 +302,10 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg_bytes = local_B * (8 * T * V + 4 * L + 12)           # logits read once + gradient written once
+    # logits read once + gradient written once (+ labels, lengths, loss).  With ragged lengths only the
+    # frames below logit_length are read; the gradient is still written for all T frames (zeros beyond the length).
+    frames_read = int(tl.clamp(0, T).sum().item())
+    alg_bytes = 4 * V * (frames_read + local_B * T) + local_B * (4 * L + 12)
     if stage_ms:
         dom = max(stage_ms, key=stage_ms.get)
         dom_ms = stage_ms[dom]
@@ -304,29 +327,99 @@ def main():
                 "kernel_ms": dom_ms, "stage_ms": stage_ms,
                 "path_achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "path_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak}
 
+    # ---- the other scaling mode, measured in the same run (N > 1 only; at N = 1 the two coincide) ----
+    secondary = None
+    if world > 1 and not args.no_secondary and not on_device:
+        if args.scaling == "strong":
+            sB, s_global, s_name = B, B * world, "weak"
+        else:
+            b0, b1 = shard_bounds(B, world, rank)
+            sB, s_global, s_name = b1 - b0, B, "strong"
+        g2 = torch.Generator(device=dev).manual_seed(2000 + rank)
+        x2 = torch.empty((sB, T, V), dtype=torch.float32, device=dev).normal_(generator=g2)
+        lab2 = torch.randint(1, V, (sB, L), generator=g2, dtype=torch.int32, device=dev)
+        tl2 = torch.full((sB,), T, dtype=torch.int32, device=dev)
+        ll2 = torch.full((sB,), L, dtype=torch.int32, device=dev)
+        if args.ragged:
+            tl2 = torch.randint(T // 2, T + 1, (sB,), generator=g2, dtype=torch.int32, device=dev)
+            ll2 = torch.randint(L // 2, L + 1, (sB,), generator=g2, dtype=torch.int32, device=dev)
+        d2 = _lib.make_desc(x2, lab2, 0, vid, L + 1, _lib.FORCE_STAGED if args.staged else 0)
+        ws2 = torch.empty(max(lib.ctcb200_workspace_bytes(ctypes.byref(d2), _lib.WS_LOSS_GRAD_LOGITS), 256), dtype=torch.uint8, device=dev)
+        loss2, grad2 = torch.empty((sB,), dtype=torch.float32, device=dev), torch.empty_like(x2)
+
+        def step2():
+            _lib.check(lib.ctcb200_loss_grad(ctypes.byref(d2), P(x2), P(lab2), P(ll2), P(tl2), None, P(loss2), P(grad2), None,
+                                             P(ws2), ws2.numel(), ctypes.c_void_p(stream.cuda_stream)))
+        for _ in range(max(args.warmup, 3)):
+            step2()
+        sync_all()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            step2()
+        f1.record(stream)
+        sync_all()
+        t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms2 = float(t2.item()) / args.steps
+        secondary = {"scaling": s_name, "value": s_global / (ms2 * 1e-3), "unit": "samples/s", "ms_per_step": ms2,
+                     "per_gpu_batch": sB, "global_batch": s_global}
+        del x2, grad2, ws2
+
     # ---- end to end: pinned host buffers -> C ABI host entry point -> loss back on the host ----
     e2e = None
     if not args.no_e2e:
         del grad, ws
         torch.cuda.empty_cache()
-        ctx = _lib.HostContext(local_B, T, V, L, 0, vid, L + 1, device=local_rank, num_slices=8)
+        bind_to_gpu_numa_node(local_rank)
+        n_slices = max(1, min(8, local_B // 16))     # >= 16 utterances per slice: below that the T-step chain, not the copy, paces a slice
+        ctx = _lib.HostContext(local_B, T, V, L, 0, vid, L + 1, device=local_rank, num_slices=n_slices)
         pin = [t.pin_memory() for t in (logits_h, labels_h, ll_h, tl_h)]
         loss_pin = torch.empty((local_B,), dtype=torch.float32).pin_memory()
+
+        def timed_e2e(grad_out):
+            for _ in range(2):
+                ctx.loss_grad(*pin, loss_pin, grad_out)
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                ctx.loss_grad(*pin, loss_pin, grad_out)          # blocks until the results are in host memory
+            dt = (time.perf_counter() - t0) / args.e2e_steps
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        dt = timed_e2e(None)
+        h2d = int(sum(p.numel() * p.element_size() for p in pin))
+        e2e = {"value": global_B / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(loss_pin.numel() * 4), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "returns": "loss [B] to the host; the gradient stays resident on the device for the optimizer "
+                          "(ctcb200_host_grad_device_ptr) -- see with_gradient_to_host for the full round trip",
+               "api": f"ctcb200_host_loss_grad (pinned host buffers, {n_slices} slices; H2D stream + kernel stream + D2H stream)"}
+        assert torch.equal(loss_pin, loss.cpu()), "host entry point disagrees with the device entry point"
+        # the same call with the [B,T,V] gradient copied back to pinned host memory as well (PCIe is full duplex: the
+        # read-back of slice i overlaps the upload of slice i+1)
+        grad_pin = torch.empty((local_B, T, V), dtype=torch.float32).pin_memory()
+        dtg = timed_e2e(grad_pin)
+        e2e["with_gradient_to_host"] = {"value": global_B / dtg, "unit": "samples/s", "ms_per_step": dtg * 1e3,
+                                        "d2h_bytes_per_step": int(loss_pin.numel() * 4 + grad_pin.numel() * 4)}
+        # the ceiling next to it: the bare host->device copy of the same pinned bytes, all ranks at once, no kernel
+        dst = torch.empty_like(logits)
         for _ in range(2):
-            ctx.loss_grad(*pin, loss_pin)
+            dst.copy_(pin[0], non_blocking=True)
         sync_all()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            ctx.loss_grad(*pin, loss_pin)          # blocks until the loss is in host memory
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dst.copy_(pin[0], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        tc = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": global_B / float(tt.item()), "unit": "samples/s",
-               "h2d_bytes_per_step": int(sum(p.numel() * p.element_size() for p in pin)),
-               "d2h_bytes_per_step": int(loss_pin.numel() * 4), "ms_per_step": float(tt.item()) * 1e3,
-               "steps": args.e2e_steps, "api": "ctcb200_host_loss_grad (pinned host buffers, 8 slices, copy stream + compute stream)"}
-        assert torch.equal(loss_pin, loss.cpu()), "host entry point disagrees with the device entry point"
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        e2e["h2d_copy_only"] = {"ms_per_step": float(tc.item()) * 1e3, "gb_per_s_per_gpu": pin[0].numel() * 4 / float(tc.item()) / 1e9,
+                                "note": "cudaMemcpyAsync of the same logits from pinned memory on every rank at once (max over ranks): "
+                                        "the PCIe / host-memory ceiling of the e2e figure"}
+        del dst, grad_pin
         ctx.close()
 
     cpu = None
@@ -346,7 +439,7 @@ def main():
                        "per_gpu_batch": local_B, "global_batch": global_B, "ragged": bool(args.ragged),
                        "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs exceed L2 (logits+grad per step >> 126 MB), no flush needed"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "secondary": secondary,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
         }), file=out, flush=True)
     if world > 1:

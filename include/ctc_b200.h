@@ -69,7 +69,11 @@ extern "C" {
 #define CTCB200_WS_HESSIAN 2
 /* ctcb200_loss_grad called with grad_logits != NULL and grad_logprobas == NULL (the training call): when the fused kernel
  * serves the shape this is about a third of CTCB200_WS_LOSS_GRAD (no gathered rows, one state tensor instead of two);
- * otherwise the two are equal.  A workspace sized with CTCB200_WS_LOSS_GRAD is always accepted as well. */
+ * otherwise the two are equal.  A workspace sized with CTCB200_WS_LOSS_GRAD is always accepted as well.
+ * NOTE: this size is NOT monotonic in B -- the kernel choice depends on the batch size (narrow vocabularies, V < 64, take
+ * the fused kernel from 80 utterances on and the larger staged scratch below that), so a caller that sizes one workspace
+ * for its largest batch and then passes smaller batches must size with CTCB200_WS_LOSS_GRAD, or take the maximum over the
+ * batch sizes it will use (ctcb200_host_create does the latter for its tail slice). */
 #define CTCB200_WS_LOSS_GRAD_LOGITS 3
 #define CTCB200_WS_HVP_LOGITS 4       /* ctcb200_hvp_logits */
 #define CTCB200_WS_DECODE 5           /* ctcb200_greedy_decode */
@@ -88,11 +92,19 @@ typedef struct ctcb200_desc {
 
 int ctcb200_version(void);
 const char* ctcb200_strerror(int code);
+/* the CUDA runtime's message for the failure behind the last CTCB200_ERR_CUDA returned on the calling thread */
+const char* ctcb200_last_cuda_error(void);
 
 /* Comma-separated stage (kernel) names ctcb200_loss_grad runs for this descriptor (the fused kernel is a single
  * stage), and the number of kernels one full call enqueues. */
 const char* ctcb200_stage_names(const ctcb200_desc* desc);
 int ctcb200_launches_per_call(const ctcb200_desc* desc);
+
+/* Developer / test hook: pins the fused kernel's plan (row workers per side, row buffers per worker, extra phase-A row
+ * buffer 0/1, ring depth in frames, split = one CTA per side in a two-CTA cluster) for every later call in this process,
+ * so a test can walk every plan on one shape; plans that do not fit are ignored.  workers = 0 restores the built-in
+ * choice.  Not part of the reference-facing surface. */
+void ctcb200_debug_fused_plan(int workers, int row_buffers, int extra_phase_a_buffer, int ring_depth, int split);
 
 /* Bytes of device workspace needed by the entry point named by `what` (CTCB200_WS_*); 0 on a bad descriptor. */
 size_t ctcb200_workspace_bytes(const ctcb200_desc* desc, int what);
@@ -105,11 +117,25 @@ size_t ctcb200_workspace_bytes(const ctcb200_desc* desc, int what);
  *   loss           [B] out: per-sample loss, +inf when the label cannot be emitted
  *   grad_logits    [B,T,V] out or NULL: d(sum_b d_loss[b]*loss[b]) / d logits  (= d_loss*(softmax*sum(occ) - occ))
  *   grad_logprobas [B,T,V] out or NULL: d_loss * ClassicCtcLossData.gradient   (= -d_loss*occupancy, base_loss.py:268)
+ * With both gradient pointers NULL only the loss is computed (forward_fn, base_loss.py:140-155): where the fused kernel
+ * serves the shape this costs half a call (the recursions meet in the middle, where the normaliser is known).
  */
 int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
                       const int32_t* label_length, const int32_t* logit_length, const float* d_loss, float* loss,
                       float* grad_logits, float* grad_logprobas, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/*
+ * log(-gradient) per (frame, token), computed in the log domain.  Replaces BaseCtcLossData.logarithmic_logproba_gradient
+ * (base_loss.py:270-298 = loss + _combine_transition_probabilities, classic_ctc_loss.py:565-669 /
+ * simplified_ctc_loss.py:456-534, with the segment log-sum-exp of tools.py:95-119): finite down to the smallest alignment
+ * weight (where exp underflows, below about -87), -inf exactly where a (frame, token) pair is impossible, for frames
+ * t >= logit_length and for infeasible samples.  log_gradient [B,T,V] out; loss [B] out or NULL; workspace sized with
+ * CTCB200_WS_LOSS_GRAD.
+ */
+int ctcb200_log_gradient(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                         const int32_t* label_length, const int32_t* logit_length, float* loss, float* log_gradient,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * alpha / beta state tensors.  Replaces ClassicCtcLossData.alpha/.beta (classic_ctc_loss.py:310-462, layout
@@ -170,9 +196,9 @@ int ctcb200_greedy_decode(const ctcb200_desc* desc, const float* logits, const i
 
 /*
  * Host-buffer convenience path (what a framework without device tensors, or the end-to-end benchmark, calls):
- * owns its device buffers, copies the HOST inputs to the device in batch slices on two streams so copies overlap
- * the kernels, and copies loss (and optionally grad_logits) back.  All pointers are HOST pointers (pinned memory
- * gives full PCIe bandwidth).  The gradient stays resident on the device (ctcb200_host_grad_device_ptr) unless
+ * owns its device buffers, copies the HOST inputs to the device in batch slices and pipelines three streams (host->device
+ * copies, kernels, device->host copies) so both PCIe directions overlap the kernels, and copies loss (and optionally
+ * grad_logits) back.  All pointers are HOST pointers (pinned memory gives full PCIe bandwidth).  The gradient stays resident on the device (ctcb200_host_grad_device_ptr) unless
  * host_grad_logits is non-NULL.  Blocks until the results are in the host buffers.
  */
 typedef struct ctcb200_host_ctx ctcb200_host_ctx;

@@ -263,6 +263,100 @@ def test_upstream_gradient_inside_the_kernels(variant, kernel_path):
 
 
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_loss_only_call_equals_the_loss_of_the_full_call(variant, kernel_path):
+    """forward_fn (base_loss.py:140-155) computes the loss alone; here that is ctcb200_loss_grad with both gradient pointers
+    NULL (the fused kernel stops at the middle of the sequence).  Same losses as the full call, +inf included."""
+    from tf_seq2seq_losses_b200 import _lib
+    B, T, V, L = 7, 41, 96, 11
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=5)
+    ll[2], tl[2] = 11, 6                      # infeasible
+    tl[3] = 0
+    ll[4] = 0
+    x, lab, llc, tlc = _cuda(logits), _cuda(labels), _cuda(ll), _cuda(tl)
+    desc = _lib.make_desc(x, lab, 0, variant, L + 1)
+    only = _lib.loss_only(desc, x, lab, llc, tlc).cpu().numpy()
+    full, _, _ = _lib.loss_grad(desc, x, lab, llc, tlc)
+    want_loss, _, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, variant)
+    _loss_close(only, want_loss)
+    _loss_close(only, full.cpu().numpy())
+    with torch.no_grad():                     # the public face under no_grad is the same call
+        _loss_close(_fn(variant)(lab, x, llc, tlc, 0).cpu().numpy(), want_loss)
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_logarithmic_logproba_gradient_is_native_log_domain(variant):
+    """base_loss.py:270-298: log occupancies are finite wherever a (frame, token) pair is possible -- also where the
+    occupancy itself underflows float32 (log below -87 / -103) -- and -inf exactly elsewhere."""
+    B, T, V, L = 3, 24, 12, 6
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=77, ragged=False)
+    logits *= 30.0                            # very peaky frames: most alignments have weights far below e^-100
+    tl[1] = 17
+    ll[2], tl[2] = 6, 4                       # infeasible sample: all -inf
+    data, lp = _data_obj((logits, labels, ll, tl), variant)
+    ref = orc.CtcLossData(labels, lp.cpu().numpy().astype(np.float64), ll, tl, 0, variant)
+    want = ref.logarithmic_logproba_gradient
+    got = data.logarithmic_logproba_gradient.cpu().numpy().astype(np.float64)
+    assert np.array_equal(np.isneginf(got), np.isneginf(want))
+    fin = np.isfinite(want)
+    assert (want[fin] < -110.0).any(), "the case must reach below float32's exp underflow"
+    assert np.max(np.abs(got[fin] - want[fin]) / np.maximum(1.0, np.abs(want[fin]))) <= 2e-5
+    # and exp(.) of it is the gradient the other entry point returns
+    assert np.max(np.abs(np.exp(got) + data.gradient.cpu().numpy())) <= GRAD_ATOL_SHORT
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_cuda_graph_capture_and_replay(variant):
+    """The reference runs under tf.function / autograph (tests/test_simplified_ctc_loss.py:293-320,
+    tests/test_hessian.py:213-257).  The equivalent here: loss + backward captured in a torch.cuda.CUDAGraph (no host
+    synchronisation, no allocation outside the graph's pool) and replayed on new data, bit-identical to the eager call."""
+    B, T, V, L = 6, 50, 128, 10
+    fn = _fn(variant)
+    logits0, labels, ll, tl = random_inputs(B, T, V, L, seed=41)
+    logits1 = random_inputs(B, T, V, L, seed=42)[0]
+    lab, llc, tlc = _cuda(labels), _cuda(ll), _cuda(tl)
+    w = _cuda(np.linspace(0.5, 2.0, B).astype(np.float32))
+
+    def eager(logits):
+        x = _cuda(logits).requires_grad_(True)
+        loss = fn(lab, x, llc, tlc, 0, max_label_length=L)
+        (torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)) * w).sum().backward()
+        return loss.detach().clone(), x.grad.clone()
+
+    want0, want1 = eager(logits0), eager(logits1)
+    static_x = _cuda(logits0).requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                # warm-up on a side stream, as torch's capture recipe asks
+        for _ in range(2):
+            static_x.grad = None
+            loss = fn(lab, static_x, llc, tlc, 0, max_label_length=L)
+            (torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)) * w).sum().backward()
+    torch.cuda.current_stream().wait_stream(side)
+    static_x.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_loss = fn(lab, static_x, llc, tlc, 0, max_label_length=L)
+        (torch.where(torch.isfinite(static_loss), static_loss, torch.zeros_like(static_loss)) * w).sum().backward()
+    for logits, want in ((logits1, want1), (logits0, want0), (logits1, want1)):
+        with torch.no_grad():
+            static_x.copy_(_cuda(logits))
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_loss.detach(), want[0])
+        assert torch.equal(static_x.grad, want[1])
+    # device-resident lengths without max_label_length: no read-back during capture (U falls back to labels.shape[1] + 1)
+    graph2 = torch.cuda.CUDAGraph()
+    with torch.no_grad():
+        fn(lab, static_x, llc, tlc, 0)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph2):
+            loss2 = fn(lab, static_x, llc, tlc, 0)
+        graph2.replay()
+        torch.cuda.synchronize()
+    _loss_close(loss2.cpu().numpy(), want1[0].cpu().numpy())
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
 def test_undefined_inputs_do_not_fault(variant, kernel_path):
     """Inputs the reference leaves undefined: label_length > labels.shape[1] (the reference pads with
     the blank as a *real* label), a real label equal to the blank, labels >= V or negative, logit_length > T, negative
@@ -279,6 +373,27 @@ def test_undefined_inputs_do_not_fault(variant, kernel_path):
     torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)).sum().backward()
     torch.cuda.synchronize()
     assert not torch.isnan(loss).any() and not torch.isnan(x.grad).any()
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+def test_real_label_equal_to_blank_matches_reference_semantics(variant, kernel_path):
+    """A real label equal to the blank is undefined input, but the reference's arithmetic is still definite: the label's
+    log-probability feeds the recursion like any other (base_loss.py:328-344) and its emission occupancy is dropped by the
+    blank-column override (classic_ctc_loss.py:647-654).  Both device paths follow the oracle's restatement of exactly
+    that, so the same utterance cannot change its loss when a batch-size heuristic picks the other kernel."""
+    B, T, V, L = 4, 14, 64, 6
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=33, ragged=False)
+    labels[1, 2] = 0
+    labels[2, 0] = 0
+    labels[2, 1] = 0
+    labels[3, 5] = 0
+    want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, variant)
+    assert np.isfinite(want_loss).all()
+    x = _cuda(logits).requires_grad_(True)
+    loss = _fn(variant)(_cuda(labels), x, _cuda(ll), _cuda(tl), 0)
+    loss.sum().backward()
+    _loss_close(loss.detach().cpu().numpy(), want_loss)
+    assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= GRAD_ATOL_SHORT
 
 
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
@@ -624,6 +739,25 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     ctx.close()
 
 
+def test_host_buffer_entry_point_uneven_tail_of_a_narrow_vocabulary():
+    """The training-call workspace is not monotonic in the batch size: with V < 64 a full slice of 81 utterances takes the
+    fused kernel (small scratch) while the 79-utterance tail takes the staged kernels (three times larger).  The host
+    context sizes its workspace for both."""
+    from tf_seq2seq_losses_b200 import _lib
+    B, T, V, L = 241, 30, 32, 8
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=10)
+    ctx = _lib.HostContext(B, T, V, L, 0, CLASSIC, L + 1, device=0, num_slices=3)      # slices of 81, 81, 79
+    pin = lambda a: torch.as_tensor(a).pin_memory()
+    loss_h = torch.empty((B,), dtype=torch.float32).pin_memory()
+    grad_h = torch.empty((B, T, V), dtype=torch.float32).pin_memory()
+    ctx.loss_grad(pin(logits), pin(labels), pin(ll), pin(tl), loss_h, grad_h)
+    ctx.close()
+    want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, CLASSIC)
+    _loss_close(loss_h.numpy(), want_loss)
+    want_grad[np.isinf(want_loss)] = 0.0
+    assert np.max(np.abs(grad_h.numpy() - want_grad)) <= GRAD_ATOL_SHORT
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # randomized shape sweep: every frame count / label length / worker configuration corner of the fused kernel
 # ------------------------------------------------------------------------------------------------------------------
@@ -687,26 +821,31 @@ def test_midsize_random_sweep(variant, kernel_path):
 
 
 @pytest.mark.parametrize("variant", [SIMPLIFIED, CLASSIC])
-@pytest.mark.parametrize("cfg", [(1, 2, 0, 2), (1, 2, 0, 1), (2, 2, 0, 4), (2, 2, 0, 2), (2, 3, 0, 3), (3, 2, 1, 6), (3, 3, 0, 4),
-                                 (4, 2, 0, 8), (4, 2, 1, 8), (4, 2, 0, 6), (4, 2, 1, 5), (4, 2, 0, 4)],
-                         ids=lambda c: "W%d_SL%d_XA%d_R%d" % c if isinstance(c, tuple) else str(c))
-def test_fused_worker_configurations(cfg, variant, monkeypatch):
-    """Every (workers per side, row buffers, extra phase-A buffer, ring depth) plan of the fused kernel gives the same
+@pytest.mark.parametrize("cfg", [(1, 2, 0, 2, 0), (1, 2, 0, 1, 0), (2, 2, 0, 4, 0), (2, 2, 0, 2, 0), (2, 3, 0, 3, 0), (3, 2, 1, 6, 0),
+                                 (3, 3, 0, 4, 0), (4, 2, 0, 8, 0), (4, 2, 1, 8, 0), (4, 2, 0, 6, 0), (4, 2, 1, 5, 0), (4, 2, 0, 4, 0),
+                                 (8, 3, 1, 16, 1), (8, 2, 0, 16, 1), (8, 2, 1, 9, 1), (6, 3, 1, 12, 1), (5, 2, 0, 5, 1), (4, 3, 1, 8, 1),
+                                 (2, 2, 0, 3, 1), (1, 2, 0, 1, 1)],
+                         ids=lambda c: "W%d_SL%d_XA%d_R%d_split%d" % c if isinstance(c, tuple) else str(c))
+def test_fused_worker_configurations(cfg, variant):
+    """Every (workers per side, row buffers, extra phase-A buffer, ring depth, split) plan of the fused kernel gives the same
     answer -- including the shortest rings (depth = workers per side, and a single slot), for which the exchange vectors
-    of the middle may or may not alias the input rings."""
+    of the middle may or may not alias the input rings, and the split plans (a two-CTA cluster per utterance)."""
     from tf_seq2seq_losses_b200 import _lib
-    monkeypatch.setenv("CTCB200_FUSED_W", str(cfg[0]))
-    monkeypatch.setenv("CTCB200_FUSED_SL", str(cfg[1]))
-    monkeypatch.setenv("CTCB200_FUSED_XA", str(cfg[2]))
-    monkeypatch.setenv("CTCB200_FUSED_R", str(cfg[3]))
+    lib = _lib.load()
+    lib.ctcb200_debug_fused_plan(*cfg)
     old = _lib.DEFAULT_FLAGS
     _lib.DEFAULT_FLAGS = _lib.FORCE_FUSED
     fn = _pkg().simple_ctc_loss if variant == SIMPLIFIED else _pkg().classic_ctc_loss
     try:
-        for (B, T, V, L, seed) in [(5, 61, 96, 20, 0), (3, 30, 37, 9, 1), (2, 7, 64, 70, 2)]:
+        for (B, T, V, L, seed) in [(5, 61, 96, 20, 0), (3, 30, 37, 9, 1), (2, 7, 64, 70, 2), (3, 45, 64, 14, 3)]:
+            if cfg[4] and V % 4:
+                continue                 # the split plans need TMA-movable rows (V % 4 == 0)
             logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
             if L == 70:
                 ll[:] = [2, 70]          # 71 label states (3 per lane) over 7 frames: one feasible, one infeasible sample
+            if seed == 3:
+                labels[:, 5:9] = labels[:, 1:5]      # repeated tokens: the leader / follower chains of the scatter plan
+                labels[0, 9] = labels[0, 1]
             want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, variant)
             x = _cuda(logits).requires_grad_(True)
             loss = fn(_cuda(labels), x, _cuda(ll), _cuda(tl), 0)
@@ -716,6 +855,7 @@ def test_fused_worker_configurations(cfg, variant, monkeypatch):
             assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= GRAD_ATOL_SHORT
     finally:
         _lib.DEFAULT_FLAGS = old
+        lib.ctcb200_debug_fused_plan(0, 0, 0, 0, 0)
 
 
 def test_size_limits_both_paths():

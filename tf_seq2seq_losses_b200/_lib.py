@@ -25,10 +25,10 @@ _LIB_NAME = "libctc_b200.so"
 _LIB_PATH = os.environ.get("CTCB200_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME))
 
 EXPORTED_SYMBOLS = (
-    "ctcb200_version", "ctcb200_strerror", "ctcb200_stage_names", "ctcb200_launches_per_call",
+    "ctcb200_version", "ctcb200_strerror", "ctcb200_last_cuda_error", "ctcb200_log_gradient", "ctcb200_stage_names", "ctcb200_launches_per_call",
     "ctcb200_workspace_bytes", "ctcb200_loss_grad", "ctcb200_states",
     "ctcb200_hessian", "ctcb200_hvp", "ctcb200_hvp_logits", "ctcb200_gamma", "ctcb200_greedy_decode", "ctcb200_host_create", "ctcb200_host_loss_grad",
-    "ctcb200_host_grad_device_ptr", "ctcb200_host_destroy",
+    "ctcb200_host_grad_device_ptr", "ctcb200_host_destroy", "ctcb200_debug_fused_plan",
 )
 
 
@@ -61,8 +61,11 @@ def load() -> ctypes.CDLL:
     lib.ctcb200_version.restype = ctypes.c_int
     lib.ctcb200_strerror.restype = ctypes.c_char_p
     lib.ctcb200_strerror.argtypes = [ctypes.c_int]
+    lib.ctcb200_last_cuda_error.restype = ctypes.c_char_p
     lib.ctcb200_stage_names.restype = ctypes.c_char_p
     lib.ctcb200_stage_names.argtypes = [dp]
+    lib.ctcb200_log_gradient.restype = ctypes.c_int
+    lib.ctcb200_log_gradient.argtypes = [dp, fp, i32p, i32p, i32p, fp, fp, vp, ctypes.c_size_t, vp]
     lib.ctcb200_launches_per_call.restype = ctypes.c_int
     lib.ctcb200_launches_per_call.argtypes = [dp]
     lib.ctcb200_workspace_bytes.restype = ctypes.c_size_t
@@ -89,13 +92,16 @@ def load() -> ctypes.CDLL:
     lib.ctcb200_host_grad_device_ptr.argtypes = [vp]
     lib.ctcb200_host_destroy.restype = None
     lib.ctcb200_host_destroy.argtypes = [vp]
+    lib.ctcb200_debug_fused_plan.restype = None
+    lib.ctcb200_debug_fused_plan.argtypes = [ctypes.c_int] * 5
     _lib = lib
     return lib
 
 
 def check(code: int) -> None:
     if code != 0:
-        raise CtcB200Error(f"libctc_b200: {load().ctcb200_strerror(code).decode()} (code {code})")
+        detail = f": {load().ctcb200_last_cuda_error().decode()}" if code == -5 else ""
+        raise CtcB200Error(f"libctc_b200: {load().ctcb200_strerror(code).decode()}{detail} (code {code})")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -107,13 +113,32 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
         raise CtcB200Error(f"{name} must live on a CUDA device: libctc_b200 has no CPU path")
 
 
+# One workspace per (device, stream), grown on demand and reused by every later call on that stream: calls on one stream
+# are ordered, so they can share scratch; no allocation happens on the steady-state path and the address is stable, which
+# is what lets a call sit inside a captured CUDA graph.
+_WORKSPACES: dict = {}
+
+
 def _workspace(desc: Desc, what: int, device: torch.device) -> torch.Tensor:
     n = load().ctcb200_workspace_bytes(ctypes.byref(desc), what)
     if n == 0 and desc.B > 0:
         raise CtcB200Error("libctc_b200: descriptor rejected (unsupported size: more than "
                            f"{MAX_STATES} label states or {MAX_TOKENS} tokens, or an invalid field)")
-    # torch's caching allocator returns 512-byte aligned blocks; the ABI needs 256
-    return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
+    n = max(int(n), 256)
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < n:
+        # torch's caching allocator returns 512-byte aligned blocks; the ABI needs 256
+        ws = torch.empty(n, dtype=torch.uint8, device=device)
+        if not torch.cuda.is_current_stream_capturing():     # memory from a graph's private pool stays with that graph
+            _WORKSPACES[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    """Drops the cached per-stream workspaces (they are re-created on the next call)."""
+    _WORKSPACES.clear()
 
 
 # Flags OR-ed into every descriptor built by make_desc.  Tests set this to FORCE_STAGED to exercise the three staged
@@ -149,6 +174,32 @@ def loss_grad(desc: Desc, logits, labels, label_length, logit_length, d_loss=Non
                                        _ptr(logit_length), _ptr(d_loss), _ptr(loss), _ptr(gl), _ptr(gp),
                                        _ptr(ws), ws.numel(), _stream(dev)))
     return loss, gl, gp
+
+
+def loss_only(desc: Desc, logits, labels, label_length, logit_length):
+    """ctcb200_loss_grad with both gradient pointers NULL: the loss alone (half a call where the fused kernel applies)."""
+    _require_cuda(logits, "logits")
+    dev = logits.device
+    loss = torch.empty((desc.B,), dtype=torch.float32, device=dev)
+    ws = _workspace(desc, WS_LOSS_GRAD_LOGITS, dev)
+    with torch.cuda.device(dev):
+        check(load().ctcb200_loss_grad(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
+                                       _ptr(logit_length), None, _ptr(loss), None, None, _ptr(ws), ws.numel(), _stream(dev)))
+    return loss
+
+
+def log_gradient(desc: Desc, logits, labels, label_length, logit_length):
+    """ctcb200_log_gradient.  Returns (log_gradient [B,T,V], loss [B])."""
+    _require_cuda(logits, "logits")
+    dev = logits.device
+    out = torch.empty((desc.B, desc.T, desc.V), dtype=torch.float32, device=dev)
+    loss = torch.empty((desc.B,), dtype=torch.float32, device=dev)
+    ws = _workspace(desc, WS_LOSS_GRAD, dev)
+    if desc.B > 0:
+        with torch.cuda.device(dev):
+            check(load().ctcb200_log_gradient(ctypes.byref(desc), _ptr(logits), _ptr(labels), _ptr(label_length),
+                                              _ptr(logit_length), _ptr(loss), _ptr(out), _ptr(ws), ws.numel(), _stream(dev)))
+    return out, loss
 
 
 def states(desc: Desc, logits, labels, label_length, logit_length):

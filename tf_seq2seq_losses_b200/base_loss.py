@@ -34,13 +34,23 @@ def _blank_to_int(blank_index) -> int:
     return int(blank_index)
 
 
-def _max_label_length_plus_one(label_length: torch.Tensor, max_label_length: Optional[int]) -> int:
-    """base_loss.py:478-486 (reduce_max_with_default with default 0).  Reads label_length back unless the caller
-    passes ``max_label_length`` (a keyword extension that avoids the device->host sync)."""
+def _max_label_length_plus_one(label_length: torch.Tensor, max_label_length: Optional[int], labels_width: int) -> int:
+    """base_loss.py:478-486 (reduce_max_with_default with default 0): the number of label states U.
+
+    Any U >= max(label_length) + 1 gives the same loss and gradient (states beyond an utterance's label are unreachable);
+    U only sets how many states the kernels carry.  So no device->host read-back is ever *needed*:
+      * ``max_label_length`` (keyword extension) is trusted when given -- it must not be smaller than the true maximum,
+        labels beyond it are cut off (the kernels clamp label_length to U - 1);
+      * host-resident lengths are reduced on the host;
+      * device-resident lengths are read back (one small synchronising copy) -- except while a CUDA graph is being
+        captured, where the bound labels.shape[1] + 1 is used instead.
+    """
     if max_label_length is not None:
         return int(max_label_length) + 1
     if label_length.numel() == 0:
         return 1
+    if label_length.is_cuda and torch.cuda.is_current_stream_capturing():
+        return int(labels_width) + 1
     return max(int(label_length.max().item()), 0) + 1
 
 
@@ -112,7 +122,8 @@ class BaseCtcLossData:
         self._labels32 = _as_int32(self._original_label, dev)
         self._label_length32 = _as_int32(self._original_label_length, dev)
         self._logit_length32 = _as_int32(self._logit_length, dev)
-        self._U = _max_label_length_plus_one(self._original_label_length, max_label_length)
+        self._U = _max_label_length_plus_one(self._original_label_length, max_label_length,
+                                             self._original_label.shape[1])
         self._desc = _lib.make_desc(self._lp, self._labels32, self._blank_index, self._variant, self._U,
                                     _lib.INPUT_LOGPROBAS)
 
@@ -155,8 +166,9 @@ class BaseCtcLossData:
 
     @cached_property
     def logarithmic_logproba_gradient(self) -> torch.Tensor:
-        """log(-gradient), [B,T,V]  (base_loss.py:270-298)."""
-        return torch.log(-self.gradient)
+        """log(-gradient), [B,T,V]  (base_loss.py:270-298), computed in the log domain on the device: finite wherever a
+        (frame, token) pair is possible at all -- also far below exp's underflow at -87 -- and -inf exactly elsewhere."""
+        return _lib.log_gradient(self._desc, *self._args())[0]
 
     @cached_property
     def hessian(self) -> torch.Tensor:
@@ -200,49 +212,57 @@ def ctc_loss_from_logproba(labels, logprobas, label_length, logit_length, blank_
 
 # ---- fused logits path (the hot path): log-softmax + loss + d/dlogits in one library call ---------------------
 class _FusedLossFn(torch.autograd.Function):
-    """ctc_loss (base_loss.py:38-68) with the log-softmax (tools.py:27-40) and its backward fused into the kernels."""
+    """ctc_loss (base_loss.py:38-68) with the log-softmax (tools.py:27-40) and its backward fused into the kernels.
+
+    Like the reference's forward_fn (base_loss.py:140-155) the forward pass computes the loss alone -- a loss-only call of
+    the fused kernel, half the work -- and the gradient is produced in the backward pass, where the upstream gradient
+    d_loss is known and is applied inside the kernel (no [B,T,V] tensor is kept between the passes, none is re-scaled)."""
 
     @staticmethod
     def forward(ctx, logits, labels, label_length, logit_length, desc):
-        x = logits.detach().contiguous()
-        loss, grad, _ = _lib.loss_grad(desc, x, labels, label_length, logit_length)
+        loss = _lib.loss_only(desc, logits.detach().contiguous(), labels, label_length, logit_length)
         ctx.desc, ctx.aux = desc, (labels, label_length, logit_length)
-        ctx.save_for_backward(logits, grad)
+        ctx.save_for_backward(logits)
         return loss
 
     @staticmethod
     def backward(ctx, d_loss):
-        logits, grad = ctx.saved_tensors
-        return _FusedGradFn.apply(logits, d_loss, grad, ctx.desc, ctx.aux), None, None, None, None
+        (logits,) = ctx.saved_tensors
+        return _FusedGradFn.apply(logits, d_loss, ctx.desc, ctx.aux), None, None, None, None
 
 
 class _FusedGradFn(torch.autograd.Function):
-    """d_loss * d loss / d logits, differentiable once more (Hessian w.r.t. logits)."""
+    """d_loss * d loss / d logits (one fused loss+gradient call with d_loss applied in the kernel), differentiable once
+    more (Hessian w.r.t. logits)."""
 
     @staticmethod
-    def forward(ctx, logits, d_loss, grad, desc, aux):
+    def forward(ctx, logits, d_loss, desc, aux):
         ctx.desc, ctx.aux = desc, aux
-        ctx.save_for_backward(logits, d_loss, grad)
-        if desc.flags & _lib.TIME_MAJOR:
-            return d_loss[None, :, None] * grad
-        return d_loss[:, None, None] * grad
+        ctx.save_for_backward(logits, d_loss)
+        labels, label_length, logit_length = aux
+        dl = d_loss.detach().to(torch.float32).contiguous()
+        _, grad, _ = _lib.loss_grad(desc, logits.detach().contiguous(), labels, label_length, logit_length, d_loss=dl)
+        return grad
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, v):
-        logits, d_loss, grad = ctx.saved_tensors
+        logits, d_loss = ctx.saved_tensors
         labels, label_length, logit_length = ctx.aux
         time_major = bool(ctx.desc.flags & _lib.TIME_MAJOR)
         if time_major and ctx.needs_input_grad[0]:
             raise NotImplementedError("second derivative w.r.t. time-major logits: pass batch-major logits")
+        x = logits.detach().contiguous()
         d_logits = None
         if ctx.needs_input_grad[0]:
             # (d2 loss / d logits2) v = J^T H J v - s (p.v - p p^T v), J = I - 1 p^T per frame: one library call
             # (ctcb200_hvp_logits: K1, K2, K3, hvp_pre, K4<HVP>, hvp_post)
-            d_logits = _lib.hvp_logits(ctx.desc, logits.detach().contiguous(), labels, label_length, logit_length, v,
-                                       d_loss)
-        d_d_loss = (v * grad).sum(dim=(0, 2) if time_major else (1, 2)) if ctx.needs_input_grad[1] else None
-        return d_logits, d_d_loss, None, None, None
+            d_logits = _lib.hvp_logits(ctx.desc, x, labels, label_length, logit_length, v, d_loss)
+        d_d_loss = None
+        if ctx.needs_input_grad[1]:      # the cotangent of d_loss: <v, d loss / d logits> per utterance
+            _, grad, _ = _lib.loss_grad(ctx.desc, x, labels, label_length, logit_length)
+            d_d_loss = (v * grad).sum(dim=(0, 2) if time_major else (1, 2))
+        return d_logits, d_d_loss, None, None
 
 
 def ctc_loss(labels, logits, label_length, logit_length, blank_index, ctc_loss_data_cls,
@@ -257,7 +277,7 @@ def ctc_loss(labels, logits, label_length, logit_length, blank_index, ctc_loss_d
     assert logits.shape[1 if logits_time_major else 0] == labels_t.shape[0] == ll_t.shape[0] == tl_t.shape[0]
     dev = logits.device
     labels32, ll32, tl32 = _as_int32(labels_t, dev), _as_int32(ll_t, dev), _as_int32(tl_t, dev)
-    U = _max_label_length_plus_one(ll_t, max_label_length)
+    U = _max_label_length_plus_one(ll_t, max_label_length, labels_t.shape[1])
     desc = _lib.make_desc(logits, labels32, _blank_to_int(blank_index), ctc_loss_data_cls._variant, U,
                           _lib.TIME_MAJOR if logits_time_major else 0)
     return _FusedLossFn.apply(logits, labels32, ll32, tl32, desc)

@@ -113,9 +113,14 @@ static int check_common(const ctcb200_desc* desc, Problem* p, int what, const fl
   return CTCB200_OK;
 }
 
+// the CUDA status behind the last CTCB200_ERR_CUDA returned on this thread (ctcb200_last_cuda_error)
+static thread_local cudaError_t t_last_cuda_error = cudaSuccess;
+
 #define CTCB200_CUDA(call)                       \
   do {                                           \
-    if ((call) != cudaSuccess) {                 \
+    const cudaError_t e__ = (call);              \
+    if (e__ != cudaSuccess) {                    \
+      t_last_cuda_error = e__;                   \
       (void)cudaGetLastError();                  \
       return CTCB200_ERR_CUDA;                   \
     }                                            \
@@ -142,6 +147,8 @@ const char* ctcb200_strerror(int code) {
   }
 }
 
+const char* ctcb200_last_cuda_error(void) { return cudaGetErrorString(t_last_cuda_error); }
+
 const char* ctcb200_stage_names(const ctcb200_desc* desc) {
   Problem p;
   if (make_problem(desc, &p) == CTCB200_OK && fused_workers(desc, p) > 0) return "kf_fused";
@@ -153,6 +160,10 @@ int ctcb200_launches_per_call(const ctcb200_desc* desc) {
   if (make_problem(desc, &p) != CTCB200_OK || p.B == 0) return 0;
   if (fused_workers(desc, p) > 0) return 1;
   return (p.T > 0 ? 1 : 0) + 1 + (p.T > 0 ? 1 : 0);
+}
+
+void ctcb200_debug_fused_plan(int workers, int row_buffers, int extra_phase_a_buffer, int ring_depth, int split) {
+  fused_set_plan_override(workers, row_buffers, extra_phase_a_buffer, ring_depth, split);
 }
 
 size_t ctcb200_workspace_bytes(const ctcb200_desc* desc, int what) {
@@ -167,8 +178,9 @@ int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32
                       float* grad_logits, float* grad_logprobas, void* workspace, size_t workspace_bytes,
                       void* stream) {
   Problem p; Scratch s;
-  // loss + d/dlogits alone is the fused kernel's call (when its plan fits) and then needs the smaller workspace only
-  const bool logits_only = grad_logits != nullptr && grad_logprobas == nullptr;
+  // loss + d/dlogits alone -- or the loss alone -- is the fused kernel's call (when its plan fits) and then needs the
+  // smaller workspace only
+  const bool logits_only = grad_logprobas == nullptr;
   int rc = check_common(desc, &p, logits_only ? CTCB200_WS_LOSS_GRAD_LOGITS : CTCB200_WS_LOSS_GRAD, logits, labels,
                         label_length, logit_length, workspace, workspace_bytes, &s, nullptr);
   if (rc != CTCB200_OK) return rc;
@@ -184,6 +196,23 @@ int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32
   if (stages == 0 || (stages & 1u)) CTCB200_CUDA(launch_softmax_gather(p, s, st));
   if (stages == 0 || (stages & 2u)) CTCB200_CUDA(launch_recursion(p, s, loss_out, false, st));
   if (stages == 0 || (stages & 4u)) CTCB200_CUDA(launch_grad(p, s, d_loss, grad_logits, grad_logprobas, st));
+  return CTCB200_OK;
+}
+
+int ctcb200_log_gradient(const ctcb200_desc* desc, const float* logits, const int32_t* labels,
+                         const int32_t* label_length, const int32_t* logit_length, float* loss, float* log_gradient,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  Problem p; Scratch s;
+  int rc = check_common(desc, &p, CTCB200_WS_LOSS_GRAD, logits, labels, label_length, logit_length, workspace,
+                        workspace_bytes, &s, nullptr);
+  if (rc != CTCB200_OK) return rc;
+  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
+  if (p.B == 0) return CTCB200_OK;
+  if (log_gradient == nullptr && p.T > 0) return CTCB200_ERR_NULL_POINTER;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CTCB200_CUDA(launch_softmax_gather(p, s, st));
+  CTCB200_CUDA(launch_recursion(p, s, loss ? loss : s.loss, false, st));
+  CTCB200_CUDA(launch_log_grad(p, s, log_gradient, st));
   return CTCB200_OK;
 }
 

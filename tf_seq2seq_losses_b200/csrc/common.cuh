@@ -131,7 +131,9 @@ cudaError_t launch_softmax_gather(const Problem& p, const Scratch& s, cudaStream
 cudaError_t launch_recursion(const Problem& p, const Scratch& s, float* loss, bool full_states, cudaStream_t st);
 cudaError_t launch_grad(const Problem& p, const Scratch& s, const float* d_loss, float* grad_logits,
                         float* grad_logprobas, cudaStream_t st);
+cudaError_t launch_log_grad(const Problem& p, const Scratch& s, float* log_grad, cudaStream_t st);
 int fused_pick_workers(const Problem& p);
+void fused_set_plan_override(int W, int SL, int XA, int R, int split);
 cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss, float* loss, float* grad, int W,
                          cudaStream_t st);
 cudaError_t launch_export_states(const Problem& p, const Scratch& s, float* alpha, float* beta, cudaStream_t st);

@@ -1,7 +1,9 @@
 // Host-buffer entry points of libctc_b200.so (include/ctc_b200.h): the call a host without device tensors makes.
-// The batch is cut into slices.  All host->device copies go back to back on one copy stream (the PCIe link never idles
-// between slices); each slice's kernels and its loss read-back run on a second stream as soon as that slice's event
-// fires, so everything but the last slice's kernel hides under the copies.
+// The batch is cut into slices and three streams form a pipeline: all host->device copies go back to back on the first
+// (the PCIe link never idles between slices), each slice's kernels run on the second as soon as that slice's event
+// fires, and the loss (and, when asked for, the gradient) of a finished slice travels device->host on the third, so the
+// two PCIe directions run concurrently and everything but the last slice's kernel and read-back hides under the copies.
+#include <initializer_list>
 #include <new>
 
 #include "common.cuh"
@@ -10,8 +12,9 @@ struct ctcb200_host_ctx {
   ctcb200_desc desc;
   int device;
   int num_slices;
-  cudaStream_t streams[2];      // [0] copies host -> device, [1] kernels and device -> host
+  cudaStream_t streams[3];      // [0] copies host -> device, [1] kernels, [2] copies device -> host
   cudaEvent_t* landed;          // [num_slices] slice i is on the device
+  cudaEvent_t* done;            // [num_slices] slice i's kernels have finished
   float* d_logits;
   float* d_grad;
   int32_t* d_labels;
@@ -27,15 +30,16 @@ extern "C" {
 void ctcb200_host_destroy(ctcb200_host_ctx* c) {
   if (c == nullptr) return;
   cudaSetDevice(c->device);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i)
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+  for (int i = 0; i < 2; ++i)
     if (c->ws[i]) cudaFree(c->ws[i]);
-  }
-  if (c->landed) {
-    for (int i = 0; i < c->num_slices; ++i)
-      if (c->landed[i]) cudaEventDestroy(c->landed[i]);
-    delete[] c->landed;
-  }
+  for (cudaEvent_t* ev : {c->landed, c->done})
+    if (ev) {
+      for (int i = 0; i < c->num_slices; ++i)
+        if (ev[i]) cudaEventDestroy(ev[i]);
+      delete[] ev;
+    }
   cudaFree(c->d_logits); cudaFree(c->d_grad); cudaFree(c->d_labels); cudaFree(c->d_label_length);
   cudaFree(c->d_logit_length); cudaFree(c->d_loss);
   delete c;
@@ -48,20 +52,30 @@ int ctcb200_host_create(const ctcb200_desc* desc, int device, int num_slices, ct
   if (num_slices < 1) num_slices = 1;
   if (desc->B > 0 && num_slices > desc->B) num_slices = desc->B;
   const int slice_b = desc->B > 0 ? (desc->B + num_slices - 1) / num_slices : 0;
+  // The training-call workspace is NOT monotonic in the batch size (a short tail slice of a narrow vocabulary falls back
+  // from the fused kernel to the larger staged scratch, see ctc_b200.h): size it for the full slice and for the tail.
   ctcb200_desc sd = *desc;
   sd.B = slice_b;
-  const size_t ws_bytes = ctcb200_workspace_bytes(&sd, CTCB200_WS_LOSS_GRAD_LOGITS);
+  size_t ws_bytes = ctcb200_workspace_bytes(&sd, CTCB200_WS_LOSS_GRAD_LOGITS);
   if (ws_bytes == 0 && slice_b > 0) return CTCB200_ERR_BAD_DESCRIPTOR;
+  if (slice_b > 0 && desc->B % slice_b != 0) {
+    sd.B = desc->B % slice_b;
+    const size_t tail = ctcb200_workspace_bytes(&sd, CTCB200_WS_LOSS_GRAD_LOGITS);
+    if (tail > ws_bytes) ws_bytes = tail;
+  }
   ctcb200_host_ctx* c = new (std::nothrow) ctcb200_host_ctx();
   if (c == nullptr) return CTCB200_ERR_CUDA;
   c->desc = *desc; c->device = device; c->num_slices = num_slices; c->ws_bytes = ws_bytes;
   const size_t n = (size_t)desc->B * desc->T * desc->V;
   bool ok = cudaSetDevice(device) == cudaSuccess;
-  for (int i = 0; i < 2 && ok; ++i) ok = ok && cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 3 && ok; ++i) ok = ok && cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaMalloc(&c->ws[0], ws_bytes ? ws_bytes : 256) == cudaSuccess;     // kernels run in order: one workspace
   c->landed = new (std::nothrow) cudaEvent_t[num_slices]();
-  ok = ok && c->landed != nullptr;
-  for (int i = 0; i < num_slices && ok; ++i) ok = ok && cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming) == cudaSuccess;
+  c->done = new (std::nothrow) cudaEvent_t[num_slices]();
+  ok = ok && c->landed != nullptr && c->done != nullptr;
+  for (int i = 0; i < num_slices && ok; ++i)
+    ok = ok && cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_logits, n ? n * 4 : 256) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_grad, n ? n * 4 : 256) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_labels, (size_t)desc->B * desc->Lw * 4 + 256) == cudaSuccess;
@@ -92,7 +106,7 @@ int ctcb200_host_loss_grad(ctcb200_host_ctx* c, const float* host_logits, const 
   const int slice_b = (d.B + c->num_slices - 1) / c->num_slices;
   const size_t tv = (size_t)d.T * d.V;
   int rc = CTCB200_OK;
-  cudaStream_t copy = c->streams[0], run = c->streams[1];
+  cudaStream_t copy = c->streams[0], run = c->streams[1], back = c->streams[2];
   for (int i = 0, b0 = 0; b0 < d.B; ++i, b0 += slice_b) {
     const int nb = (d.B - b0 < slice_b) ? d.B - b0 : slice_b;
     ctcb200_desc sd = d;
@@ -109,12 +123,13 @@ int ctcb200_host_loss_grad(ctcb200_host_ctx* c, const float* host_logits, const 
                            c->d_logit_length + b0, nullptr, c->d_loss + b0, c->d_grad + b0 * tv, nullptr,
                            c->ws[0], c->ws_bytes, run);
     if (rc != CTCB200_OK) break;
-    ok = cudaMemcpyAsync(host_loss + b0, c->d_loss + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, run) == cudaSuccess;
+    ok = cudaEventRecord(c->done[i], run) == cudaSuccess && cudaStreamWaitEvent(back, c->done[i], 0) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(host_loss + b0, c->d_loss + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, back) == cudaSuccess;
     if (host_grad_logits && tv)
-      ok = ok && cudaMemcpyAsync(host_grad_logits + b0 * tv, c->d_grad + b0 * tv, nb * tv * 4, cudaMemcpyDeviceToHost, run) == cudaSuccess;
+      ok = ok && cudaMemcpyAsync(host_grad_logits + b0 * tv, c->d_grad + b0 * tv, nb * tv * 4, cudaMemcpyDeviceToHost, back) == cudaSuccess;
     if (!ok) { rc = CTCB200_ERR_CUDA; break; }
   }
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 3; ++i)
     if (cudaStreamSynchronize(c->streams[i]) != cudaSuccess) rc = CTCB200_ERR_CUDA;
   if (rc == CTCB200_ERR_CUDA) (void)cudaGetLastError();
   return rc;

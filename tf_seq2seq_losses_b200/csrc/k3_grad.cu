@@ -131,6 +131,93 @@ __global__ void __launch_bounds__(kK3Warps * kWarp)
   }
 }
 
+// K3-log: the same frames in the log domain -> logarithmic_logproba_gradient (base_loss.py:270-298): log of the
+// occupancy per (frame, token), -inf where impossible, for frames beyond logit_length and for infeasible samples.
+template <int NS, bool CLASSIC>
+__global__ void __launch_bounds__(kK3Warps * kWarp)
+    k3_log_grad(Problem p, Scratch s, float* __restrict__ log_grad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int Vpad = (p.V + 7) & ~7;
+  unsigned short* map = reinterpret_cast<unsigned short*>(smem_raw);
+  int* toks = reinterpret_cast<int*>(smem_raw + (size_t)Vpad * sizeof(unsigned short));
+  int* mx_all = toks + p.Upad;
+  float* sm_all = reinterpret_cast<float*>(mx_all + kK3Warps * p.Upad);
+
+  const int kK3Rows = k3_rows(p);
+  const int tiles = (p.T + kK3Rows - 1) / kK3Rows;
+  const int b = blockIdx.x / tiles, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t_begin = (blockIdx.x % tiles) * kK3Rows, t_end = min(p.T, t_begin + kK3Rows);
+  const int L = utt_label_len(p, b), n_t = utt_frames(p, b);
+  const double lossd = s.lossd[b];
+  const bool dead = (lossd == (double)INFINITY) || (t_begin >= n_t);
+  if (!dead) build_utterance_tables(p, b, L, toks, map, Vpad);
+  const size_t row_pitch = (size_t)(CLASSIC ? 2 : 1) * p.Upad;
+  int* mx = mx_all + (size_t)warp * p.Upad;
+  float* sm = sm_all + (size_t)warp * p.Upad;
+  for (int t = t_begin + warp; t < t_end; t += kK3Warps) {
+    const size_t row = (size_t)b * p.T + t;
+    float* out = log_grad + row_offset(p, b, t);
+    if (dead || t >= n_t) {
+      for (int k = lane; k < p.V; k += kWarp) out[k] = kNegInf;
+      continue;
+    }
+    const float* A = s.alphaT + ((size_t)b * (p.T + 1) + t) * row_pitch;
+    const float* Bn = s.betaT + ((size_t)b * (p.T + 1) + t + 1) * row_pitch;
+    const size_t crow = (size_t)b * (p.T + 1) + t;
+    const double lossb = lossd + s.ca[crow] + s.cb[crow + 1];
+    const float lg_blank = row_log_occupancies_t<NS, CLASSIC>(p, L, lane, A, Bn, s.dT + row * p.Upad, s.h[row], lossb, toks,
+                                                              map, mx, sm);
+    for (int k = lane; k < p.V; k += kWarp) {
+      const unsigned short m = map[k];
+      float v = kNegInf;
+      if (k == p.blank) v = lg_blank;
+      else if (m != kNoSlot && sm[m] > 0.0f) v = (float)(lossb + (double)float_unorder(mx[m])) + __logf(sm[m]);
+      out[k] = v;
+    }
+    __syncwarp();
+  }
+}
+
+size_t log_grad_smem_bytes(const Problem& p) {
+  const int Vpad = (p.V + 7) & ~7;
+  return (size_t)Vpad * sizeof(unsigned short) + (size_t)p.Upad * sizeof(int) + (size_t)kK3Warps * p.Upad * 8;
+}
+
+template <int NS>
+static cudaError_t launch_k3_log_ns(const Problem& p, const Scratch& s, float* log_grad, cudaStream_t st) {
+  const size_t smem = log_grad_smem_bytes(p);
+  const int kK3Rows = k3_rows(p);
+  const unsigned grid = (unsigned)(((p.T + kK3Rows - 1) / kK3Rows) * (long long)p.B);
+  cudaError_t e;
+  if (p.variant == CTCB200_CLASSIC) {
+    if (smem > 48 * 1024 &&
+        (e = cudaFuncSetAttribute(k3_log_grad<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return e;
+    k3_log_grad<NS, true><<<grid, kK3Warps * kWarp, smem, st>>>(p, s, log_grad);
+  } else {
+    if (smem > 48 * 1024 &&
+        (e = cudaFuncSetAttribute(k3_log_grad<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return e;
+    k3_log_grad<NS, false><<<grid, kK3Warps * kWarp, smem, st>>>(p, s, log_grad);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_log_grad(const Problem& p, const Scratch& s, float* log_grad, cudaStream_t st) {
+  if (p.B == 0 || p.T == 0 || log_grad == nullptr) return cudaSuccess;
+  switch (p.NS) {
+#define CTCB200_CASE(n) \
+  case n:               \
+    return launch_k3_log_ns<n>(p, s, log_grad, st);
+    CTCB200_CASE(1) CTCB200_CASE(2) CTCB200_CASE(3) CTCB200_CASE(4) CTCB200_CASE(5) CTCB200_CASE(6)
+    CTCB200_CASE(7) CTCB200_CASE(8) CTCB200_CASE(9) CTCB200_CASE(10) CTCB200_CASE(11) CTCB200_CASE(12)
+    CTCB200_CASE(13) CTCB200_CASE(14) CTCB200_CASE(15) CTCB200_CASE(16)
+#undef CTCB200_CASE
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
 size_t grad_smem_bytes(const Problem& p) {
   const int Vpad = (p.V + 7) & ~7;
   return (size_t)Vpad * sizeof(unsigned short) + (size_t)p.Upad * sizeof(int) +

@@ -3,32 +3,50 @@
 
 namespace ctcb200 {
 
-// (workers per side, row buffers per worker, extra phase-A buffer, ring depth) for this problem; W == 0 when the fused
-// kernel cannot take it.  Preference: configurations that leave room for two CTAs per SM (more warps to hide latency),
-// then one CTA per SM.
-static bool fused_pick(const Problem& p, int* W, int* SL, int* XA, int* R) {
-  *W = 0; *SL = 0; *XA = 0; *R = 0;
+// Developer / test hook (ctcb200_debug_fused_plan in ctc_b200.h): a process-wide override of the plan below.
+static int g_plan_override[5] = {0, 0, 0, 0, 0};     // W, SL, XA, R, split; W == 0: no override
+void fused_set_plan_override(int W, int SL, int XA, int R, int split) {
+  const int v[5] = {W, SL, XA, R, split};
+  for (int i = 4; i >= 0; --i) __atomic_store_n(&g_plan_override[i], v[i], __ATOMIC_RELEASE);   // W last
+}
+
+// One SM holds 228 KB of shared memory and every resident CTA reserves 1 KB of it; one CTA may opt in to 227 KB.
+constexpr int kSmemHalfSm = 228 * 1024 / 2 - 1024;
+constexpr int kNumSms = 148;
+
+// (workers per side, row buffers per worker, extra phase-A buffer, ring depth, split) for this problem; W == 0 when the
+// fused kernel cannot take it.
+//   B > 74   one CTA per utterance, both sides inside (W <= 4): prefer plans that leave room for two CTAs per SM.
+//   B <= 74  split: a cluster of two CTAs per utterance, one side each (W <= 8), every CTA with an SM to itself.  Needs
+//            TMA-movable rows (`tma_ok`).  Measured at T=1000 V=1024 L=200 (simplified): B=32 323 vs 427 us, B=64 323 vs
+//            431 us; two split CTAs sharing an SM (B=128) lose to the one-CTA plan, 640 vs 440 us.
+static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, int* R, int* split) {
+  *W = 0; *SL = 0; *XA = 0; *R = 0; *split = 0;
   if (p.NS > kMaxNS) return false;
-  // developer override for experiments: CTCB200_FUSED_W / CTCB200_FUSED_SL / CTCB200_FUSED_XA / CTCB200_FUSED_R
-  const char* ew = getenv("CTCB200_FUSED_W");
-  const char* es = getenv("CTCB200_FUSED_SL");
-  const char* ex = getenv("CTCB200_FUSED_XA");
-  const char* er = getenv("CTCB200_FUSED_R");
-  if (ew != nullptr && es != nullptr) {
-    const int w = atoi(ew), sl = atoi(es), xa = ex ? atoi(ex) : 0, r = er ? atoi(er) : 2 * w;
-    if (w >= 1 && w <= kMaxWorkers && sl >= 2 && sl <= 3 && xa >= 0 && xa <= 1 && r >= w && r <= 2 * w &&
-        fused_layout(p.V, p.Upad, p.S, w, sl, xa, r).total <= kSmemPerSm) {
-      *W = w; *SL = sl; *XA = xa; *R = r;
+  const int ow = __atomic_load_n(&g_plan_override[0], __ATOMIC_ACQUIRE);
+  if (ow > 0) {
+    const int sl = g_plan_override[1], xa = g_plan_override[2], r = g_plan_override[3], sp = g_plan_override[4] ? 1 : 0;
+    if (ow <= (sp ? kMaxWorkersSplit : kMaxWorkers) && sl >= 2 && sl <= 3 && xa >= 0 && xa <= 1 && r >= 1 && r <= 2 * ow &&
+        (!sp || tma_ok) && fused_layout(p.V, p.Upad, p.S, ow, sl, xa, r, sp ? 1 : 2).total <= kSmemPerSm) {
+      *W = ow; *SL = sl; *XA = xa; *R = r; *split = sp;
       return true;
     }
+  }
+  if (tma_ok && 2 * p.B <= kNumSms) {
+    static const int scand[8][4] = {{8, 3, 1, 16}, {8, 2, 1, 16}, {8, 2, 0, 16}, {6, 3, 1, 12}, {6, 2, 1, 12}, {6, 2, 0, 12},
+                                    {4, 3, 1, 8}, {4, 2, 0, 8}};
+    for (int c = 0; c < 8; ++c)
+      if (fused_layout(p.V, p.Upad, p.S, scand[c][0], scand[c][1], scand[c][2], scand[c][3], 1).total <= kSmemPerSm) {
+        *W = scand[c][0]; *SL = scand[c][1]; *XA = scand[c][2]; *R = scand[c][3]; *split = 1;
+        return true;
+      }
   }
   // {workers per side, row buffers per worker, extra phase-A row buffer, ring depth}.  Measured on B200 (B=256 T=1000
   // V=1024): 4 workers beat 3 for both variants; the classic variant (two state planes) only fits 4 workers next to a
   // second CTA with a 6-frame ring.
   static const int cand[11][4] = {{4, 2, 1, 8}, {4, 2, 0, 8}, {4, 2, 0, 6}, {3, 3, 1, 6}, {3, 3, 0, 6}, {3, 2, 1, 6},
                                   {3, 2, 0, 6}, {2, 3, 0, 4}, {2, 2, 0, 4}, {1, 2, 0, 2}, {1, 2, 0, 1}};
-  // an SM has 228 KB of shared memory and every resident CTA reserves 1 KB of it; one CTA may opt in to 227 KB
-  const int budgets[2] = {228 * 1024 / 2 - 1024, kSmemPerSm};
+  const int budgets[2] = {kSmemHalfSm, kSmemPerSm};
   for (int bi = 0; bi < 2; ++bi)
     for (int c = 0; c < 11; ++c) {
       if (fused_layout(p.V, p.Upad, p.S, cand[c][0], cand[c][1], cand[c][2], cand[c][3]).total <= budgets[bi]) {
@@ -40,8 +58,8 @@ static bool fused_pick(const Problem& p, int* W, int* SL, int* XA, int* R) {
 }
 
 int fused_pick_workers(const Problem& p) {
-  int W, SL, XA, R;
-  fused_pick(p, &W, &SL, &XA, &R);
+  int W, SL, XA, R, split;
+  fused_pick(p, false, &W, &SL, &XA, &R, &split);     // eligibility does not depend on the row mover
   return W;
 }
 
@@ -60,9 +78,9 @@ cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss
 #ifdef CTCB200_FUSED_TIMING
   a.dbg = reinterpret_cast<long long*>(s.betaT);   // the staged path's beta scratch is unused by the fused kernel
 #endif
-  fused_pick(p, &a.W, &a.SL, &a.XA, &a.R);
-  (void)W;
   a.tma = ((p.V & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0) ? 1 : 0;
+  fused_pick(p, a.tma != 0, &a.W, &a.SL, &a.XA, &a.R, &a.split);
+  (void)W;
   const bool classic = p.variant == CTCB200_CLASSIC;
   if (classic) return a.tma ? launch_fused_variant<true, true>(a, st) : launch_fused_variant<true, false>(a, st);
   return a.tma ? launch_fused_variant<false, true>(a, st) : launch_fused_variant<false, false>(a, st);

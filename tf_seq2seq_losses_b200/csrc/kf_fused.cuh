@@ -23,9 +23,11 @@
 //                    row in shared memory (double buffered), the warp reduces it (phase A: row log-sum-exp), gathers
 //                    the <= U label columns into the ring, and in phase B combines alpha*beta into per-token
 //                    occupancies (occupancy.cuh) and streams out the dense gradient row with 128-bit stores.
-// Warps hand work to each other through monotonic counters in shared memory (st.release / ld.acquire at CTA scope);
-// there is no CTA-wide barrier inside a phase.
+// Warps hand frames to each other through rings of mbarriers in shared memory (full_d / full_s / empty, see SideView): a
+// waiting warp is suspended by the hardware (mbarrier.try_wait), nobody spins on a counter, and there is no CTA-wide
+// barrier inside a phase.
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -37,7 +39,8 @@ namespace ctcb200 {
 
 constexpr int kMaxRowSlots = 4;     // row buffers per worker: current + prefetch(es); phase A may own one more (see XA)
 constexpr int kFusedGroup = 4;      // frames per unrolled group (renormalisation cadence, see recursion.cuh)
-constexpr int kMaxWorkers = 4;
+constexpr int kMaxWorkers = 4;       // workers per side when one CTA serves both sides of an utterance
+constexpr int kMaxWorkersSplit = 8;  // ... when each side has a CTA (and an SM, or half of one) to itself: see SPLIT below
 
 // ---- PTX helpers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -46,6 +49,25 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// thread-block cluster primitives (split mode: the two sides of an utterance are the two CTAs of a cluster)
+__device__ __forceinline__ void cluster_sync_all() {     // every thread of every CTA of the cluster; release / acquire
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_map(unsigned smem_addr, unsigned cta_rank) {   // my address -> the peer's copy
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_dsmem_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -81,6 +103,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #ifndef CTCB200_L2_HINTS
 #define CTCB200_L2_HINTS 0
 #endif
+
 #ifndef CTCB200_L2_ROW_HINTS
 #define CTCB200_L2_ROW_HINTS CTCB200_L2_HINTS
 #endif
@@ -210,7 +233,8 @@ __host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a *
 // stbuf in phase B), which is what lets 4 workers x 3 row buffers fit next to a second CTA on the SM.
 // R = ring depth in frames (>= W; 2W unless shared memory is short).  The exchange vectors of the middle (S*Upad floats
 // per side, used only between the phases) alias each side's own input ring when that is large enough.
-__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL, int XA, int R) {
+// `sides` = 2 when one CTA holds both sides of the utterance, 1 in split mode (a CTA per side).
+__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL, int XA, int R, int sides = 2) {
   FusedLayout f;
   f.W = W;
   f.R = R;
@@ -219,7 +243,7 @@ __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int 
   const int Vp = (V + 3) & ~3;
   int o = 0;
   f.xch_aliased = (R >= S) ? 1 : 0;       // a side's exchange vector (S*Upad floats) fits its input ring (R*Upad floats)
-  f.off_xch = o;  o += f.xch_aliased ? 0 : 2 * S * Upad * 4;
+  f.off_xch = o;  o += f.xch_aliased ? 0 : sides * S * Upad * 4;
   f.off_xoff = o; o += 2 * 8;
   o = fl_align(o, 128);
   int s = 0;
@@ -238,7 +262,7 @@ __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int 
   f.s_ringh = s; s += fl_align(f.R * 4, 16);
   f.side_bytes = fl_align(s, 128);
   f.off_side0 = o;
-  f.total = o + 2 * f.side_bytes;
+  f.total = o + sides * f.side_bytes;
   return f;
 }
 
@@ -251,6 +275,7 @@ struct FusedArgs {
   float* loss;          // [B]
   float* grad;          // [B,T,V]
   int W, SL, XA, R;
+  int split;            // 1: a cluster of two CTAs per utterance, one per side (small batches); 0: one CTA per utterance
   int tma;              // 1: rows move by 1-D TMA (V % 4 == 0, 16-byte aligned bases); 0: by 4-byte cp.async / plain stores
   long long* dbg;       // [B][warps][12] when built with CTCB200_FUSED_TIMING, else unused
 };
@@ -336,15 +361,17 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
     if (!phase_b) {
       __syncwarp();
       if (lane == 0) mbar_arrive(sv.empty + slot);             // ring slot may be refilled
-      // -> global scratch for the other side's phase B
+      if (a.grad != nullptr) {      // (a loss-only call stops at the middle: nobody will read the scratch)
+        // -> global scratch for the other side's phase B
 #pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        stg_keep(g_state + j * kWarp + lane, out0[j]);
-        if (CLASSIC && SIDE == 0) stg_keep(g_state + kUpad + j * kWarp + lane, v1[j]);
+        for (int j = 0; j < NS; ++j) {
+          stg_keep(g_state + j * kWarp + lane, out0[j]);
+          if (CLASSIC && SIDE == 0) stg_keep(g_state + kUpad + j * kWarp + lane, v1[j]);
+        }
+        if (lane == 0) *g_off = c;
+        g_state += g_step;
+        g_off += t_step;
       }
-      if (lane == 0) *g_off = c;
-      g_state += g_step;
-      g_off += t_step;
     } else {
       if (i >= R) TIMED(6, mbar_wait(sv.empty + slot, use_par ^ 1u));   // previous frame of the slot is finished
       float* dst = sv.rings + slot * (S_ * kUpad);
@@ -374,17 +401,30 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
 
 __device__ __forceinline__ unsigned long long* bars_of(const SideView& sv, int w) { return sv.bar + w * kMaxRowSlots; }
 
+// Static facts about this lane's label states l = lane*NS + j, in registers for the whole kernel (bit j of each mask):
+//   ok    state l emits a token: l < label_length and the label is a valid column.  Its log-probability feeds the
+//         recursion (d[t,l], base_loss.py:328-344) whatever the token is -- including a label equal to the blank.
+//   nb    ... and that token is not the blank: its occupancy lands in the token's gradient column.  (A real label equal
+//         to the blank is undefined input; like the reference's blank_mask override, classic_ctc_loss.py:647-654, and K3,
+//         its emission occupancy is dropped from the blank column and from the row total.)
+struct LaneLabels {
+  unsigned ok_nb;       // ok | nb << 16
+  unsigned flags;       // bit 0: ok of state lane*NS-1, bit 1: its nb, bit 3: the label holds a blank-valued entry (uniform
+                        // over the CTA)
+  __device__ __forceinline__ bool ok(int j) const { return (ok_nb >> j) & 1u; }
+  __device__ __forceinline__ bool nb(int j) const { return (ok_nb >> (16 + j)) & 1u; }
+  __device__ __forceinline__ bool nb_left() const { return flags & 2u; }
+  __device__ __forceinline__ bool any_blank_label() const { return flags & 8u; }
+};
+
 // ---- row worker, one phase -------------------------------------------------------------------------------------------
-// tok[j] = cleaned label (base_loss.py:395-418) of this lane's states l = lane*NS + j (always a safe column index),
-// tok_left = label of state lane*NS - 1; bit j of okm says state l really emits tok[j] (l < label_length, token in
-// range and not the blank), ok_left the same for state lane*NS - 1.  All of it lives in registers for the whole kernel.
-// `side` is a runtime argument (one code body for both sides keeps the instruction footprint inside the instruction
-// cache).
+// tok[j] = cleaned label (base_loss.py:395-418) of this lane's states l = lane*NS + j (always a safe column index);
+// `ll` holds their static facts (LaneLabels).  `side` is a runtime argument (one code body for both sides keeps the
+// instruction footprint inside the instruction cache).
 template <int NS, bool CLASSIC, bool PHASE_B, bool TMA>
 __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int side, int b,
                                           int w, int count, int t_first, int t_step, int L, double lossd_mid, float dl,
-                                          const int (&tok)[NS], int tok_left, unsigned okm, bool ok_left, int lane,
-                                          long long* tm) {
+                                          const int (&tok)[NS], const LaneLabels ll, int lane, long long* tm) {
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   constexpr float kLog2e = 1.4426950408889634f;
   const Problem& p = a.p;
@@ -507,7 +547,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       const float mr0 = (m_run == kNegInf || m_run == INFINITY) ? 0.0f : m_run;
       const float sum = warp_sum(s_run * ex2_approx((mr0 - M0) * kLog2e));
       lse = fmaf(lg2_approx(sum), 0.6931471805599453f, M0);    // sum is in [1, V]: no denormal / range handling needed
-      if (lane == 0) a.rowlse[(size_t)b * p.T + t] = lse;
+      if (lane == 0 && a.grad != nullptr) a.rowlse[(size_t)b * p.T + t] = lse;
     }
 #ifdef CTCB200_FUSED_TIMING
     tm[6] += clock64() - t_s0;   // workers: row statistics
@@ -519,7 +559,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       float* dst = sv.ringd + slot * kUpad;
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        dd[j] = ((okm >> j) & 1u) ? row[tok[j]] - lse : kNegInf;
+        dd[j] = ll.ok(j) ? row[tok[j]] - lse : kNegInf;
         dst[j * kWarp + lane] = dd[j];
       }
     }
@@ -608,7 +648,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
         for (int j = 0; j < NS; ++j) {
           const float bn = (j < NS - 1) ? b0[j + 1] : bx;
           occ[j] = ex2_approx((K + (a0[j] + dd[j] + bn)) * kLog2e);   // emit label[l]: simplified_ctc_loss.py:503-510
-          if (!((okm >> j) & 1u)) occ[j] = 0.0f;
+          if (!ll.ok(j)) occ[j] = 0.0f;
         }
       } else {
         // alpha rows: plane 0 = x[l] (the diagonal carrier, see rec_phase), plane 1 = A[l,1]; beta rows: B[l,1]
@@ -628,11 +668,11 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           const float bn = (j < NS - 1) ? b1[j + 1] : bx;
           // diagonal step emitting label[l] (classic_ctc_loss.py:629-639); open -> open is barred on a repeat (x)
           occ[j] = ex2_approx((K + (dd[j] + xa[j] + bn)) * kLog2e);
-          if (!((okm >> j) & 1u)) occ[j] = 0.0f;
+          if (!ll.ok(j)) occ[j] = 0.0f;
           // horizontal step re-emitting label[l-1] from the open state (classic_ctc_loss.py:617-626)
           const float dp = (j > 0) ? dd[j - 1] : d_left;
           occ_stay[j] = ex2_approx((K + (a1[j] + dp + b1[j])) * kLog2e);
-          if (!((j > 0) ? (bool)((okm >> (j > 0 ? j - 1 : 0)) & 1u) : ok_left)) occ_stay[j] = 0.0f;
+          if (!((j > 0) ? ll.nb(j > 0 ? j - 1 : 0) : ll.nb_left())) occ_stay[j] = 0.0f;   // a blank is never re-emitted
         }
       }
       // Scatter the occupancies into the row: row[token] -= d_loss * occ.
@@ -652,12 +692,31 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       float osum = 0.0f;
 #pragma unroll
       for (int j = 0; j < NS; ++j) osum += occ[j];
-      // Scatter: row[token] -= d_loss * occ.  Shared-memory float atomics (a compare-and-swap loop on sm_100) were
-      // measured against shuffle-combined, conflict-mask-guarded and statically ranked conflict-free read-modify-write
-      // passes; the atomics won every time at V = 1024 and tied at V = 5000.
+      if (ll.any_blank_label()) {
+        // Undefined input (a real label equal to the blank): the reference overrides the blank column with the horizontal
+        // term alone, so the emission occupancy of such states vanishes from the row and from its total -- the softmax
+        // part, already in the row with weight 1, shrinks accordingly (same numbers as the staged kernel K3).
+        float drop = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+          if (ll.ok(j) && !ll.nb(j)) drop += occ[j];
+        drop = warp_sum(drop);
+        if (drop != 0.0f) {
+          const float keep = 1.0f - drop;
+          for (int c4 = lane; c4 < n4; c4 += kWarp) {
+            float4 v = row4[c4];
+            row4[c4] = make_float4(v.x * keep, v.y * keep, v.z * keep, v.w * keep);
+          }
+          __syncwarp();
+        }
+      }
+      // Scatter: row[token] -= d_loss * occ.  Shared-memory float atomics were measured against shuffle-combined,
+      // conflict-mask-guarded and statically ranked conflict-free read-modify-write passes (round 1) and against a static
+      // leader / follower plan that needs no atomics at all (round 2: 671 vs 573 us at B=256, 347 vs 323 us at B=32); the
+      // atomics won every time at V = 1024 and tied at V = 5000.
 #pragma unroll
       for (int j = 0; j < NS; ++j)
-        if (occ[j] > 0.0f) atomicAdd(&row[tok[j]], -dl * occ[j]);
+        if (ll.nb(j) && occ[j] > 0.0f) atomicAdd(&row[tok[j]], -dl * occ[j]);
       __syncwarp();
 #ifdef CTCB200_FUSED_TIMING
       const long long t_o2 = clock64();
@@ -688,19 +747,28 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   if (PHASE_B && tma && lane == 0) bulk_store_wait_read();      // shared memory must outlive the stores reading it
 }
 
-// ---- the kernel ---------------------------------------------------------------------------------------------------------
-template <int NS, bool CLASSIC, bool TMA>
-__global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
+// ---- the kernel body ----------------------------------------------------------------------------------------------------
+// SPLIT = false: one CTA per utterance holds both sides (2 x (1 recursion warp + W workers), W <= 4, two CTAs per SM): the
+//                plan for full batches, where the SMs are shared by two utterances and HBM bandwidth is the limit.
+// SPLIT = true : a cluster of two CTAs per utterance, one side each (1 recursion warp + W workers, W <= 8): the plan for
+//                small batches (B <= 148, e.g. the per-GPU slice of a batch sharded over 4 or 8 GPUs), where the T-step chain
+//                is the runtime.  Every side gets twice the row workers, its own shared memory and a less crowded
+//                scheduler; the sides only talk at the middle (state vectors through distributed shared memory, two cluster
+//                barriers) and through the global scratch the other side reads back in phase B.
+template <int NS, bool CLASSIC, bool TMA, bool SPLIT>
+__device__ __forceinline__ void fused_body(const FusedArgs& a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const Problem& p = a.p;
-  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA, a.R);
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA, a.R, SPLIT ? 1 : 2);
+  const int b = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = f.W;
   // Warp -> (side, role); role 0 = recursion warp, 1..W = row workers.  Other placements were measured on B200 (the two
   // recursion warps on the highest warp ids, on one scheduler, or rotated by the CTA index so co-resident CTAs do not
-  // stack roles): none beat this one (simplified +-1 %, classic 3-8 % slower).
-  const int side = warp / (W + 1), role = warp % (W + 1);
+  // stack roles): none beat this one (simplified +-1 %, classic 3-8 % slower).  In split mode the side is the CTA's rank
+  // in its cluster.
+  const int side = SPLIT ? (int)(blockIdx.x & 1u) : warp / (W + 1), role = SPLIT ? warp : warp % (W + 1);
+  const int my = SPLIT ? 0 : side;        // index of this side's block in THIS CTA's shared memory
   const int L = utt_label_len(p, b), n_t = utt_frames(p, b), M = n_t >> 1;
   const float dl = a.d_loss ? a.d_loss[b] : 1.0f;
 
@@ -709,10 +777,10 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
     return reinterpret_cast<float*>(smem + (f.xch_aliased ? f.off_side0 + s2 * f.side_bytes + f.s_ringd : f.off_xch + s2 * (S * kUpad * 4)));
   };
   double* xoff = reinterpret_cast<double*>(smem + f.off_xoff);
-  const SideView sv = side_view(smem, f, side);
+  const SideView sv = side_view(smem, f, my);
 
   auto reset_sync_state = [&]() {     // one thread: counters to zero, mbarriers to phase 0
-    for (int s2 = 0; s2 < 2; ++s2) {
+    for (int s2 = 0; s2 < (SPLIT ? 1 : 2); ++s2) {
       const SideView v = side_view(smem, f, s2);
       for (int k = 0; k < 3 * f.R; ++k) mbar_init(v.full_d + k, 1u);
       for (int k = 0; k < W * kMaxRowSlots; ++k) mbar_init(v.bar + k, TMA ? 1u : (unsigned)kWarp);
@@ -723,20 +791,29 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
   if (tid == 0) reset_sync_state();
   __syncthreads();
 
-  // this lane's labels and their static facts, in registers for the whole kernel (see worker_phase)
+  // this lane's labels and their static facts, in registers for the whole kernel (see LaneLabels)
   int tok[NS];
-  unsigned okm = 0u;
-  auto emits = [&](int l, int& t) {       // does state l emit a real token?  t <- a column index that is always safe
+  LaneLabels ll;
+  ll.ok_nb = 0u; ll.flags = 0u;
+  auto emits = [&](int l, int& t) {       // does state l emit a token?  t <- a column index that is always safe
     const int raw = utt_token(p, b, l, L);
     const bool in_range = raw >= 0 && raw < p.V;
     t = in_range ? raw : p.blank;
-    return l >= 0 && l < L && in_range && raw != p.blank;
+    return l >= 0 && l < L && in_range;
   };
 #pragma unroll
   for (int j = 0; j < NS; ++j)
-    if (emits(lane * NS + j, tok[j])) okm |= 1u << j;
-  int tok_left;
-  const bool ok_left = emits(lane * NS - 1, tok_left);
+    if (emits(lane * NS + j, tok[j])) ll.ok_nb |= (tok[j] != p.blank) ? (0x10001u << j) : (1u << j);
+  {
+    int tl;
+    if (emits(lane * NS - 1, tl)) ll.flags |= (tl != p.blank) ? 3u : 1u;
+  }
+  {
+    bool blank_label = false;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) blank_label |= ll.ok(j) && !ll.nb(j);
+    if (__syncthreads_or(blank_label)) ll.flags |= 8u;
+  }
 
   long long tm[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   (void)tm;
@@ -783,9 +860,9 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
       if (side == 0) rec_phase<NS, CLASSIC, 0>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
       else rec_phase<NS, CLASSIC, 1>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
     } else if (ph == 0) {
-      worker_phase<NS, CLASSIC, false, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, tok_left, okm, ok_left, lane, tm);
+      worker_phase<NS, CLASSIC, false, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, ll, lane, tm);
     } else {
-      worker_phase<NS, CLASSIC, true, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, tok_left, okm, ok_left, lane, tm);
+      worker_phase<NS, CLASSIC, true, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, ll, lane, tm);
     }
     if (ph == 1) break;
 #ifdef CTCB200_FUSED_TIMING
@@ -796,25 +873,45 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
     // Each recursion warp leaves its state vector in ITS OWN side's exchange slot.  When shared memory is short the slot
     // aliases that side's input ring, which is idle by now: the warp has consumed every frame its workers produced.
     if (role == 0) {
-      float* dst = xch_of(side);
+      float* dst = xch_of(my);
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         dst[j * kWarp + lane] = v0[j];
         if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
       }
-      if (lane == 0) xoff[side] = c;
+      if (lane == 0) xoff[my] = c;
     }
-    __syncthreads();     // also makes phase A's global scratch visible to the whole CTA
-    if (tid == 0) reset_sync_state();
     LseAcc zacc;
-    {
+    double off_sum;
+    if (!SPLIT) {
+      __syncthreads();     // also makes phase A's global scratch visible to the whole CTA
+      if (tid == 0) reset_sync_state();
       const float *xa = xch_of(0), *xb = xch_of(1);
       for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(xa[q] + xb[q]);
+      off_sum = xoff[0] + xoff[1];
+    } else {
+      // The other side lives in the peer CTA of the cluster: its exchange vector is read through distributed shared
+      // memory.  The cluster barrier (release / acquire) also publishes phase A's global scratch -- row log-sum-exps,
+      // stored states, offsets -- to the peer, which reads it back in phase B.
+      cluster_sync_all();
+      if (tid == 0) reset_sync_state();
+      const float* own = xch_of(0);
+      const unsigned peer = cluster_map(smem_u32(own), (unsigned)(side ^ 1));
+      for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(own[q] + ld_dsmem_f32(peer + 4u * q));
+      const double o_own = xoff[0], o_peer = ld_dsmem_f64(cluster_map(smem_u32(xoff), (unsigned)(side ^ 1)));
+      off_sum = (side == 0) ? o_own + o_peer : o_peer + o_own;     // the same double on both sides
     }
     const float lz = zacc.warp_result();
     dead = (lz == kNegInf);
-    lossd_mid = -((double)lz + xoff[0] + xoff[1]);
-    __syncthreads();
+    lossd_mid = -((double)lz + off_sum);
+    if (!SPLIT) __syncthreads();
+    else cluster_sync_all();          // the peer has read this CTA's exchange slot: phase B may overwrite it
+    if (a.grad == nullptr) {
+      // Loss-only call (the forward pass of a training step, or evaluation): -log Z is known at the middle, so the call
+      // costs phase A alone -- half the chain, one read of the logits, nothing written but the loss.
+      if (side == 0 && tid == 0) a.loss[b] = dead ? INFINITY : (float)lossd_mid;
+      return;
+    }
     if (dead) break;
   }
 
@@ -840,19 +937,76 @@ __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 :
   }
 }
 
+// ---- the two kernels ----------------------------------------------------------------------------------------------------
+template <int NS, bool CLASSIC, bool TMA>
+__global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
+  fused_body<NS, CLASSIC, TMA, false>(a);
+}
+template <int NS, bool CLASSIC, bool TMA>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__((NS <= 8) ? 112 : 224)
+    kf_fused_split(const __grid_constant__ FusedArgs a) {
+  fused_body<NS, CLASSIC, TMA, true>(a);
+}
+
 // ---- host side: one launcher per (variant, row-mover) pair, defined in kf_fused_*.cu --------------------------------
 constexpr int kSmemPerSm = 227 * 1024;
 
 template <bool CLASSIC, bool TMA>
 cudaError_t launch_fused_variant(const FusedArgs& a, cudaStream_t st);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is issued once per (kernel, device) -- or again when a later problem
+// needs more -- not on every launch.
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+static cudaError_t ensure_smem(Kernel kernel, int* cache, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (__atomic_load_n(&cache[dev], __ATOMIC_ACQUIRE) >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) {      // racing callers all set a value that is large enough for themselves; keep the maximum
+    int seen = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
+    while (seen < bytes && !__atomic_compare_exchange_n(&cache[dev], &seen, bytes, false, __ATOMIC_RELEASE, __ATOMIC_RELAXED)) {}
+  }
+  return e;
+}
+
 template <int NS, bool CLASSIC, bool TMA>
 static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
-  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA, a.R);
-  cudaError_t e = cudaFuncSetAttribute(kf_fused<NS, CLASSIC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, f.total);
-  if (e != cudaSuccess) return e;
-  kf_fused<NS, CLASSIC, TMA><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
-  return cudaGetLastError();
+  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA, a.R, a.split ? 1 : 2);
+  // NOTE: a concurrent caller on the same device may raise the attribute between this check and the launch; it is
+  // never lowered, so the launch below always finds at least f.total bytes allowed.
+  static int cache[2][kMaxDevices];
+  if (a.split) {
+    if constexpr (TMA) {       // the split plan exists for TMA-movable rows only (fused_pick never asks for it otherwise)
+      cudaError_t e = ensure_smem(kf_fused_split<NS, CLASSIC, TMA>, cache[1], f.total);
+      if (e != cudaSuccess) return e;
+      kf_fused_split<NS, CLASSIC, TMA><<<2 * a.p.B, (a.W + 1) * kWarp, f.total, st>>>(a);
+    } else {
+      return cudaErrorInvalidValue;
+    }
+  } else {
+    cudaError_t e = ensure_smem(kf_fused<NS, CLASSIC, TMA>, cache[0], f.total);
+    if (e != cudaSuccess) return e;
+    kf_fused<NS, CLASSIC, TMA><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
+  }
+  const cudaError_t err = cudaGetLastError();
+  if (err == cudaErrorLaunchOutOfResources) {      // say which resource: the plan and the compiled kernel disagree
+    cudaFuncAttributes fa{};
+    if constexpr (TMA) {
+      if (a.split) (void)cudaFuncGetAttributes(&fa, kf_fused_split<NS, CLASSIC, TMA>);
+      else (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA>);
+    } else {
+      (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA>);
+    }
+    fprintf(stderr, "libctc_b200: kf_fused%s<NS=%d,classic=%d,tma=%d> W=%d SL=%d XA=%d R=%d: %d threads, %d B dynamic smem; kernel: %d regs, "
+            "max %d threads/block, %zu B static smem, %d B max dynamic smem, %zu B local\n", a.split ? "_split" : "", NS, (int)CLASSIC,
+            (int)TMA, a.W, a.SL, a.XA, a.R, (a.split ? 1 : 2) * (a.W + 1) * kWarp, f.total, fa.numRegs, fa.maxThreadsPerBlock,
+            fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes);
+    (void)cudaGetLastError();
+  }
+  return err;
 }
 
 #define CTCB200_DEFINE_FUSED_VARIANT(CLASSIC_, TMA_)                                                        \

@@ -187,4 +187,99 @@ __device__ __forceinline__ float row_occupancies_t(const Problem& p, int L, int 
   return occ_sum;
 }
 
+// ---- the same combine in the LOG domain (logarithmic_logproba_gradient, base_loss.py:270-298) ------------------------
+// The reference returns log occupancies, finite down to the smallest alignment weight and -inf exactly where a
+// (frame, token) pair is impossible; exp(.) of them underflows below e^-87.  Per slot this is the reference's
+// unsorted_segment_logsumexp (tools.py:95-119): segment maximum first, then log sum exp(x - max).
+// Order-preserving map float <-> int so that shared-memory integer atomicMax implements a float maximum.
+__device__ __forceinline__ int float_order(float v) {
+  const int i = __float_as_int(v);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float float_unorder(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+// One warp, one frame.  Fills mx[slot] (as ordered ints) and sm[slot] so that the log occupancy of the slot's token is
+// lossb + mx + log(sm) (-inf when sm == 0), for slots 0..Upad-1; returns the blank's log occupancy.  lossb (the loss plus
+// both renormalisation offsets) stays in double until it has met the state term: the loss may be hundreds of nats while
+// the result is a small number.
+template <int NS, bool CLASSIC>
+__device__ __forceinline__ float row_log_occupancies_t(const Problem& p, int L, int lane, const float* A, const float* Bn,
+                                                       const float* d, float h, double lossb, const int* toks,
+                                                       const unsigned short* map, int* mx, float* sm) {
+  constexpr int kUpad = NS * kWarp;
+  for (int i = lane; i < kUpad; i += kWarp) {
+    mx[i] = float_order(kNegInf);
+    sm[i] = 0.0f;
+  }
+  float a0[NS], a1[NS], b0[NS], b1[NS], dv[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int pos = j * kWarp + lane;
+    a0[j] = A[pos];
+    b0[j] = Bn[pos];
+    dv[j] = d[pos];
+    if (CLASSIC) {
+      a1[j] = A[kUpad + pos];
+      b1[j] = Bn[kUpad + pos];
+    }
+  }
+  float b_up = __shfl_down_sync(kFull, CLASSIC ? b1[0] : b0[0], 1);
+  if (lane == 31) b_up = kNegInf;
+  float d_left = __shfl_up_sync(kFull, dv[NS - 1], 1);
+  if (lane == 0) d_left = kNegInf;
+  __syncwarp();
+  // log-weights of the transitions leaving / staying in this lane's states, and the slots they land in
+  float mv[NS], st[NS];
+  unsigned short s_mv[NS], s_st[NS];
+  LseAcc blank_acc;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int l = lane * NS + j;
+    mv[j] = kNegInf; st[j] = kNegInf;
+    s_mv[j] = kNoSlot; s_st[j] = kNoSlot;
+    if (l > L) continue;
+    const int tok = toks[l];
+    const unsigned short slot = (tok >= 0 && tok < p.V) ? map[tok] : kNoSlot;
+    if (!CLASSIC) {
+      blank_acc.add(a0[j] + b0[j]);
+      if (l < L && slot != kNoSlot && slot != kUpad) {
+        const float bnext = (j < NS - 1) ? b0[j < NS - 1 ? j + 1 : j] : b_up;
+        mv[j] = a0[j] + dv[j] + bnext;
+        s_mv[j] = slot;
+      }
+    } else {
+      blank_acc.add(lse2(a0[j], a1[j]) + b0[j]);
+      const int tok_prev = tok_at(p, toks, l - 1);
+      if (l < L && slot != kNoSlot && slot != kUpad) {
+        const float bnext = (j < NS - 1) ? b1[j < NS - 1 ? j + 1 : j] : b_up;
+        const float v1 = (tok == tok_prev) ? kNegInf : a1[j] + dv[j];
+        mv[j] = lse2(a0[j] + dv[j], v1) + bnext;
+        s_mv[j] = slot;
+      }
+      if (l >= 1) {
+        const unsigned short sp = (tok_prev >= 0 && tok_prev < p.V) ? map[tok_prev] : kNoSlot;
+        if (sp != kNoSlot && sp != kUpad) {
+          const float dprev = (j > 0) ? dv[j > 0 ? j - 1 : 0] : d_left;
+          st[j] = a1[j] + dprev + b1[j];
+          s_st[j] = sp;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    if (s_mv[j] != kNoSlot && mv[j] != kNegInf) atomicMax(&mx[s_mv[j]], float_order(mv[j]));
+    if (CLASSIC && s_st[j] != kNoSlot && st[j] != kNegInf) atomicMax(&mx[s_st[j]], float_order(st[j]));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    if (s_mv[j] != kNoSlot && mv[j] != kNegInf) atomicAdd(&sm[s_mv[j]], __expf(mv[j] - float_unorder(mx[s_mv[j]])));
+    if (CLASSIC && s_st[j] != kNoSlot && st[j] != kNegInf) atomicAdd(&sm[s_st[j]], __expf(st[j] - float_unorder(mx[s_st[j]])));
+  }
+  const float lb = blank_acc.warp_result();
+  __syncwarp();
+  return (lb == kNegInf || h == kNegInf) ? kNegInf : (float)(lossb + ((double)h + (double)lb));
+}
+
 }  // namespace ctcb200
