@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--staged", action="store_true", help="force the three staged kernels instead of the fused one")
     ap.add_argument("--ragged", action="store_true", help="logit_length~U[T/2,T], label_length~U[L/2,L]")
     ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--dtype-in", default="f32", choices=["f32", "bf16"],
+                    help="bf16: logits are bfloat16 in HBM / host memory (CTCB200_LOGITS_BF16, an extension of the reference's "
+                         "float32-only interface); arithmetic stays fp32.  A SECONDARY line: the headline is f32")
+    ap.add_argument("--dtype-grad", default="f32", choices=["f32", "bf16"], help="with --dtype-in bf16: gradient format")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other scaling mode's measurement at N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -242,11 +246,18 @@ def main():
     else:
         logits_h, labels_h, ll_h, tl_h = synth(local_B, T, V, L, 1000 + rank, args.ragged)
         logits, labels, ll, tl = logits_h.to(dev), labels_h.to(dev), ll_h.to(dev), tl_h.to(dev)
-    desc = _lib.make_desc(logits, labels, 0, vid, L + 1, _lib.FORCE_STAGED if args.staged else 0)
+    es_in, es_out = (2 if args.dtype_in == "bf16" else 4), (2 if args.dtype_grad == "bf16" else 4)
+    assert es_out == 4 or es_in == 2, "--dtype-grad bf16 needs --dtype-in bf16"
+    if es_in == 2:
+        logits = logits.to(torch.bfloat16)
+        if not on_device:
+            logits_h = logits_h.to(torch.bfloat16)
+    dflags = (_lib.FORCE_STAGED if args.staged else 0) | (_lib.GRAD_BF16 if es_out == 2 else 0)
+    desc = _lib.make_desc(logits, labels, 0, vid, L + 1, dflags)
     lib = _lib.load()
     ws = torch.empty(max(lib.ctcb200_workspace_bytes(ctypes.byref(desc), _lib.WS_LOSS_GRAD_LOGITS), 256), dtype=torch.uint8, device=dev)
     loss = torch.empty((local_B,), dtype=torch.float32, device=dev)
-    grad = torch.empty_like(logits)
+    grad = torch.empty(logits.shape, dtype=torch.bfloat16 if es_out == 2 else torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
 
@@ -305,7 +316,7 @@ def main():
     # logits read once + gradient written once (+ labels, lengths, loss).  With ragged lengths only the
     # frames below logit_length are read; the gradient is still written for all T frames (zeros beyond the length).
     frames_read = int(tl.clamp(0, T).sum().item())
-    alg_bytes = 4 * V * (frames_read + local_B * T) + local_B * (4 * L + 12)
+    alg_bytes = V * (es_in * frames_read + es_out * local_B * T) + local_B * (4 * L + 12)
     if stage_ms:
         dom = max(stage_ms, key=stage_ms.get)
         dom_ms = stage_ms[dom]
@@ -337,15 +348,17 @@ def main():
             sB, s_global, s_name = b1 - b0, B, "strong"
         g2 = torch.Generator(device=dev).manual_seed(2000 + rank)
         x2 = torch.empty((sB, T, V), dtype=torch.float32, device=dev).normal_(generator=g2)
+        if es_in == 2:
+            x2 = x2.to(torch.bfloat16)
         lab2 = torch.randint(1, V, (sB, L), generator=g2, dtype=torch.int32, device=dev)
         tl2 = torch.full((sB,), T, dtype=torch.int32, device=dev)
         ll2 = torch.full((sB,), L, dtype=torch.int32, device=dev)
         if args.ragged:
             tl2 = torch.randint(T // 2, T + 1, (sB,), generator=g2, dtype=torch.int32, device=dev)
             ll2 = torch.randint(L // 2, L + 1, (sB,), generator=g2, dtype=torch.int32, device=dev)
-        d2 = _lib.make_desc(x2, lab2, 0, vid, L + 1, _lib.FORCE_STAGED if args.staged else 0)
+        d2 = _lib.make_desc(x2, lab2, 0, vid, L + 1, dflags)
         ws2 = torch.empty(max(lib.ctcb200_workspace_bytes(ctypes.byref(d2), _lib.WS_LOSS_GRAD_LOGITS), 256), dtype=torch.uint8, device=dev)
-        loss2, grad2 = torch.empty((sB,), dtype=torch.float32, device=dev), torch.empty_like(x2)
+        loss2, grad2 = torch.empty((sB,), dtype=torch.float32, device=dev), torch.empty(x2.shape, dtype=grad.dtype, device=dev)
 
         def step2():
             _lib.check(lib.ctcb200_loss_grad(ctypes.byref(d2), P(x2), P(lab2), P(ll2), P(tl2), None, P(loss2), P(grad2), None,
@@ -373,7 +386,8 @@ def main():
         torch.cuda.empty_cache()
         bind_to_gpu_numa_node(local_rank)
         n_slices = max(1, min(8, local_B // 16))     # >= 16 utterances per slice: below that the T-step chain, not the copy, paces a slice
-        ctx = _lib.HostContext(local_B, T, V, L, 0, vid, L + 1, device=local_rank, num_slices=n_slices)
+        ctx = _lib.HostContext(local_B, T, V, L, 0, vid, L + 1, device=local_rank, num_slices=n_slices,
+                               flags=desc.flags & (_lib.LOGITS_BF16 | _lib.GRAD_BF16))
         pin = [t.pin_memory() for t in (logits_h, labels_h, ll_h, tl_h)]
         loss_pin = torch.empty((local_B,), dtype=torch.float32).pin_memory()
 
@@ -400,10 +414,10 @@ def main():
         assert torch.equal(loss_pin, loss.cpu()), "host entry point disagrees with the device entry point"
         # the same call with the [B,T,V] gradient copied back to pinned host memory as well (PCIe is full duplex: the
         # read-back of slice i overlaps the upload of slice i+1)
-        grad_pin = torch.empty((local_B, T, V), dtype=torch.float32).pin_memory()
+        grad_pin = torch.empty((local_B, T, V), dtype=torch.bfloat16 if es_out == 2 else torch.float32).pin_memory()
         dtg = timed_e2e(grad_pin)
         e2e["with_gradient_to_host"] = {"value": global_B / dtg, "unit": "samples/s", "ms_per_step": dtg * 1e3,
-                                        "d2h_bytes_per_step": int(loss_pin.numel() * 4 + grad_pin.numel() * 4)}
+                                        "d2h_bytes_per_step": int(loss_pin.numel() * 4 + grad_pin.numel() * es_out)}
         # the ceiling next to it: the bare host->device copy of the same pinned bytes, all ranks at once, no kernel
         dst = torch.empty_like(logits)
         for _ in range(2):
@@ -416,16 +430,17 @@ def main():
         tc = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-        e2e["h2d_copy_only"] = {"ms_per_step": float(tc.item()) * 1e3, "gb_per_s_per_gpu": pin[0].numel() * 4 / float(tc.item()) / 1e9,
+        e2e["h2d_copy_only"] = {"ms_per_step": float(tc.item()) * 1e3, "gb_per_s_per_gpu": pin[0].numel() * es_in / float(tc.item()) / 1e9,
                                 "note": "cudaMemcpyAsync of the same logits from pinned memory on every rank at once (max over ranks): "
                                         "the PCIe / host-memory ceiling of the e2e figure"}
         del dst, grad_pin
         ctx.close()
+        os.sched_setaffinity(0, affinity_before)      # the CPU baseline below uses every host core
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         nb = min(local_B, args.cpu_sample)
-        v, dt, cores = cpu_port_samples_per_s(1 if variant == "simplified" else 0, logits_h[:nb], labels_h[:nb], ll_h[:nb], tl_h[:nb], 2)
+        v, dt, cores = cpu_port_samples_per_s(1 if variant == "simplified" else 0, logits_h[:nb].float(), labels_h[:nb], ll_h[:nb], tl_h[:nb], 2)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                "sample": f"{nb} of {local_B} utterances (same T,V,L), 2 repetitions, C port of the reference algorithm in float32"}
 
@@ -433,7 +448,8 @@ def main():
         print(json.dumps({
             "metric": METRIC if args.workload == "cfg2" else f"CTC loss+grad samples/s ({args.workload})",
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32" if es_in == 4 else f"f32 arithmetic on bf16 logits ({args.dtype_grad} gradient) -- secondary line, not the headline",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {variant}_ctc_loss B={B} T={T} V={V} L={L}", "variant": variant,
                        "per_gpu_batch": local_B, "global_batch": global_B, "ragged": bool(args.ragged),

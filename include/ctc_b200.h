@@ -49,6 +49,13 @@ extern "C" {
                                       tf.nn.ctc_loss calls logits_time_major; the reference itself is batch-major only,
                                       classic_ctc_loss.py:33-39).  Every other array keeps its layout. */
 
+#define CTCB200_LOGITS_BF16 16u    /* ctcb200_loss_grad / ctcb200_host_* only (an extension: the reference asserts float32,
+                                      base_loss.py:131): `logits` points at bfloat16 [B,T,V] (or [T,B,V]).  All arithmetic stays
+                                      fp32; the HBM and PCIe bytes of the input halve.  Served by the fused kernel alone: needs
+                                      V % 8 == 0, 16-byte aligned bases, grad_logprobas == NULL, and a shape the fused plan takes
+                                      (else CTCB200_ERR_UNSUPPORTED_SIZE). */
+#define CTCB200_GRAD_BF16 32u      /* with CTCB200_LOGITS_BF16: grad_logits is written as bfloat16 too (round to nearest even) */
+
 /* Profiling aid: flags bits 8..15 select which stages of ctcb200_loss_grad are enqueued (bit 8+i = i-th name of
  * ctcb200_stage_names()); 0 = all.  A partial call must follow a full call on the same workspace and inputs. */
 #define CTCB200_STAGE_SHIFT 8
@@ -101,10 +108,11 @@ const char* ctcb200_stage_names(const ctcb200_desc* desc);
 int ctcb200_launches_per_call(const ctcb200_desc* desc);
 
 /* Developer / test hook: pins the fused kernel's plan (row workers per side, row buffers per worker, extra phase-A row
- * buffer 0/1, ring depth in frames, split = one CTA per side in a two-CTA cluster) for every later call in this process,
- * so a test can walk every plan on one shape; plans that do not fit are ignored.  workers = 0 restores the built-in
- * choice.  Not part of the reference-facing surface. */
-void ctcb200_debug_fused_plan(int workers, int row_buffers, int extra_phase_a_buffer, int ring_depth, int split);
+ * buffer 0/1, ring depth in frames, mode: bit 0 = split, one CTA per side in a two-CTA cluster; bit 1 = store every state
+ * row instead of every second one) for every later call in this process, so a test can walk every plan on one shape;
+ * plans that do not fit are ignored.  workers = 0 restores the built-in choice.  Not part of the reference-facing
+ * surface. */
+void ctcb200_debug_fused_plan(int workers, int row_buffers, int extra_phase_a_buffer, int ring_depth, int mode);
 
 /* Bytes of device workspace needed by the entry point named by `what` (CTCB200_WS_*); 0 on a bad descriptor. */
 size_t ctcb200_workspace_bytes(const ctcb200_desc* desc, int what);

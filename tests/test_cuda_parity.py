@@ -357,6 +357,48 @@ def test_cuda_graph_capture_and_replay(variant):
 
 
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
+@pytest.mark.parametrize("shape", [(6, 41, 64, 9), (3, 70, 136, 70), (70, 24, 1024, 6), (80, 30, 8, 5)],
+                         ids=lambda s: "B%dT%dV%dL%d" % s)
+def test_bfloat16_logits(shape, variant):
+    """CTCB200_LOGITS_BF16 (an extension; the reference asserts float32, base_loss.py:131): the kernels read bfloat16 rows,
+    widen them on the fly and compute in fp32, so the result is the oracle's on the bf16-ROUNDED inputs -- loss and
+    float32 gradient to the usual fp32 tolerance, the bfloat16 gradient to half a bf16 ulp on top."""
+    from tf_seq2seq_losses_b200 import _lib
+    B, T, V, L = shape
+    logits, labels, ll, tl = random_inputs(B, T, V, L, seed=B + T)
+    logits *= 3.0
+    if B >= 6:
+        ll[1], tl[1] = L, max(L // 2 - 1, 0)       # infeasible
+        tl[2] = T // 2 + 1                          # padded frames
+    xb = _cuda(logits).to(torch.bfloat16)
+    rounded = xb.float().cpu().numpy()
+    want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, rounded, ll, tl, 0, variant)
+    want_grad[np.isinf(want_loss)] = 0.0
+    lab, llc, tlc = _cuda(labels), _cuda(ll), _cuda(tl)
+    atol = GRAD_ATOL_SHORT if T <= 64 else GRAD_ATOL_LONG
+    # C ABI: bf16 in, float32 gradient out
+    desc = _lib.make_desc(xb, lab, 0, variant, L + 1)
+    loss, grad, _ = _lib.loss_grad(desc, xb, lab, llc, tlc)
+    assert grad.dtype == torch.float32
+    _loss_close(loss.cpu().numpy(), want_loss)
+    assert np.max(np.abs(grad.cpu().numpy() - want_grad)) <= atol
+    _loss_close(_lib.loss_only(desc, xb, lab, llc, tlc).cpu().numpy(), want_loss)
+    # public face: bf16 in, bf16 gradient out (autograd wants the input's dtype), upstream gradient applied in the kernel
+    x = xb.clone().requires_grad_(True)
+    w = np.linspace(0.5, 2.0, B).astype(np.float32)
+    out = _fn(variant)(lab, x, llc, tlc, 0)
+    (torch.where(torch.isfinite(out), out, torch.zeros_like(out)) * _cuda(w)).sum().backward()
+    assert x.grad.dtype == torch.bfloat16
+    want_w = want_grad * w[:, None, None]
+    got = x.grad.float().cpu().numpy()
+    assert np.max(np.abs(got - want_w) - np.abs(want_w) * 2.0 ** -8) <= 2.5 * atol
+    # shapes the fused kernel cannot take are refused, not silently converted
+    bad = _cuda(logits[:, :, :V - 4]).to(torch.bfloat16).contiguous()
+    with pytest.raises(_lib.CtcB200Error):
+        _lib.loss_grad(_lib.make_desc(bad, lab, 0, variant, L + 1), bad, lab, llc, tlc)
+
+
+@pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
 def test_undefined_inputs_do_not_fault(variant, kernel_path):
     """Inputs the reference leaves undefined: label_length > labels.shape[1] (the reference pads with
     the blank as a *real* label), a real label equal to the blank, labels >= V or negative, logit_length > T, negative
@@ -824,12 +866,14 @@ def test_midsize_random_sweep(variant, kernel_path):
 @pytest.mark.parametrize("cfg", [(1, 2, 0, 2, 0), (1, 2, 0, 1, 0), (2, 2, 0, 4, 0), (2, 2, 0, 2, 0), (2, 3, 0, 3, 0), (3, 2, 1, 6, 0),
                                  (3, 3, 0, 4, 0), (4, 2, 0, 8, 0), (4, 2, 1, 8, 0), (4, 2, 0, 6, 0), (4, 2, 1, 5, 0), (4, 2, 0, 4, 0),
                                  (8, 3, 1, 16, 1), (8, 2, 0, 16, 1), (8, 2, 1, 9, 1), (6, 3, 1, 12, 1), (5, 2, 0, 5, 1), (4, 3, 1, 8, 1),
-                                 (2, 2, 0, 3, 1), (1, 2, 0, 1, 1)],
-                         ids=lambda c: "W%d_SL%d_XA%d_R%d_split%d" % c if isinstance(c, tuple) else str(c))
+                                 (2, 2, 0, 3, 1), (1, 2, 0, 1, 1), (4, 2, 1, 8, 2), (2, 2, 0, 4, 2), (8, 3, 1, 16, 3), (2, 2, 0, 2, 1)],
+                         ids=lambda c: "W%d_SL%d_XA%d_R%d_mode%d" % c if isinstance(c, tuple) else str(c))
 def test_fused_worker_configurations(cfg, variant):
-    """Every (workers per side, row buffers, extra phase-A buffer, ring depth, split) plan of the fused kernel gives the same
+    """Every (workers per side, row buffers, extra phase-A buffer, ring depth, mode) plan of the fused kernel gives the same
     answer -- including the shortest rings (depth = workers per side, and a single slot), for which the exchange vectors
-    of the middle may or may not alias the input rings, and the split plans (a two-CTA cluster per utterance)."""
+    of the middle may or may not alias the input rings, the split plans (mode bit 0: a two-CTA cluster per utterance) and
+    both state-scratch schemes (every second row, the default wherever workers and ring depth are even and the variant is
+    the simplified one; every row with mode bit 1)."""
     from tf_seq2seq_losses_b200 import _lib
     lib = _lib.load()
     lib.ctcb200_debug_fused_plan(*cfg)
@@ -838,13 +882,13 @@ def test_fused_worker_configurations(cfg, variant):
     fn = _pkg().simple_ctc_loss if variant == SIMPLIFIED else _pkg().classic_ctc_loss
     try:
         for (B, T, V, L, seed) in [(5, 61, 96, 20, 0), (3, 30, 37, 9, 1), (2, 7, 64, 70, 2), (3, 45, 64, 14, 3)]:
-            if cfg[4] and V % 4:
+            if (cfg[4] & 1) and V % 4:
                 continue                 # the split plans need TMA-movable rows (V % 4 == 0)
             logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
             if L == 70:
                 ll[:] = [2, 70]          # 71 label states (3 per lane) over 7 frames: one feasible, one infeasible sample
             if seed == 3:
-                labels[:, 5:9] = labels[:, 1:5]      # repeated tokens: the leader / follower chains of the scatter plan
+                labels[:, 5:9] = labels[:, 1:5]      # repeated tokens: several states scatter into one gradient column
                 labels[0, 9] = labels[0, 1]
             want_loss, want_grad, _ = orc.loss_and_grad_logits(labels, logits, ll, tl, 0, variant)
             x = _cuda(logits).requires_grad_(True)

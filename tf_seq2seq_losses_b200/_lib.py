@@ -17,6 +17,8 @@ INPUT_LOGPROBAS = 1
 FORCE_STAGED = 2
 FORCE_FUSED = 4
 TIME_MAJOR = 8
+LOGITS_BF16 = 16
+GRAD_BF16 = 32
 WS_LOSS_GRAD, WS_STATES, WS_HESSIAN, WS_LOSS_GRAD_LOGITS, WS_HVP_LOGITS, WS_DECODE = 0, 1, 2, 3, 4, 5
 MAX_STATES = 512
 MAX_TOKENS = 32768
@@ -149,9 +151,13 @@ DEFAULT_FLAGS = FORCE_STAGED if os.environ.get("CTCB200_FORCE_STAGED", "0") == "
 def make_desc(logits: torch.Tensor, labels: torch.Tensor, blank: int, variant: int, U: int, flags: int = 0) -> Desc:
     """Descriptor of a call on ``logits`` [B,T,V] (or [T,B,V] when ``flags`` has TIME_MAJOR)."""
     B, T, V = logits.shape
-    if int(flags) & TIME_MAJOR:
+    flags = int(flags)
+    if flags & TIME_MAJOR:
         B, T = T, B
-    return Desc(B, T, V, labels.shape[1], int(blank), int(variant), int(U), int(flags) | DEFAULT_FLAGS)
+    if logits.dtype == torch.bfloat16:
+        flags |= LOGITS_BF16          # bf16 rows exist in the fused kernel only: never combined with FORCE_STAGED
+        return Desc(B, T, V, labels.shape[1], int(blank), int(variant), int(U), flags | (DEFAULT_FLAGS & ~FORCE_STAGED))
+    return Desc(B, T, V, labels.shape[1], int(blank), int(variant), int(U), flags | DEFAULT_FLAGS)
 
 
 def _stream(device: torch.device):
@@ -166,7 +172,8 @@ def loss_grad(desc: Desc, logits, labels, label_length, logit_length, d_loss=Non
     loss = torch.empty((desc.B,), dtype=torch.float32, device=dev)
     gl = None
     if want_grad_logits:
-        gl = grad_logits_out if grad_logits_out is not None else torch.empty_like(logits)
+        gdtype = torch.bfloat16 if (desc.flags & GRAD_BF16) else torch.float32
+        gl = grad_logits_out if grad_logits_out is not None else torch.empty(logits.shape, dtype=gdtype, device=dev)
     gp = torch.empty_like(logits) if want_grad_logprobas else None
     ws = _workspace(desc, WS_LOSS_GRAD_LOGITS if (want_grad_logits and not want_grad_logprobas) else WS_LOSS_GRAD, dev)
     with torch.cuda.device(dev):
@@ -305,8 +312,8 @@ def greedy_decode(logits, logit_length, blank: int = 0, merge_repeated: bool = T
 class HostContext:
     """ctcb200_host_*: loss + gradient from HOST buffers (pinned tensors), copies overlapped with the kernels."""
 
-    def __init__(self, B, T, V, Lw, blank, variant, U, device=0, num_slices=8):
-        self.desc = Desc(B, T, V, Lw, blank, variant, U, 0)
+    def __init__(self, B, T, V, Lw, blank, variant, U, device=0, num_slices=8, flags=0):
+        self.desc = Desc(B, T, V, Lw, blank, variant, U, int(flags))
         self.device = int(device)
         handle = ctypes.c_void_p()
         check(load().ctcb200_host_create(ctypes.byref(self.desc), self.device, int(num_slices), ctypes.byref(handle)))

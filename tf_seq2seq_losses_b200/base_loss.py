@@ -252,6 +252,8 @@ class _FusedGradFn(torch.autograd.Function):
         time_major = bool(ctx.desc.flags & _lib.TIME_MAJOR)
         if time_major and ctx.needs_input_grad[0]:
             raise NotImplementedError("second derivative w.r.t. time-major logits: pass batch-major logits")
+        if (ctx.desc.flags & _lib.LOGITS_BF16) and ctx.needs_input_grad[0]:
+            raise NotImplementedError("second derivative w.r.t. bfloat16 logits: pass float32 logits")
         x = logits.detach().contiguous()
         d_logits = None
         if ctx.needs_input_grad[0]:
@@ -261,7 +263,7 @@ class _FusedGradFn(torch.autograd.Function):
         d_d_loss = None
         if ctx.needs_input_grad[1]:      # the cotangent of d_loss: <v, d loss / d logits> per utterance
             _, grad, _ = _lib.loss_grad(ctx.desc, x, labels, label_length, logit_length)
-            d_d_loss = (v * grad).sum(dim=(0, 2) if time_major else (1, 2))
+            d_d_loss = (v.float() * grad.float()).sum(dim=(0, 2) if time_major else (1, 2))
         return d_logits, d_d_loss, None, None
 
 
@@ -271,7 +273,9 @@ def ctc_loss(labels, logits, label_length, logit_length, blank_index, ctc_loss_d
     ``logits_time_major`` (keyword extension, the reference is batch-major only): ``logits`` is [T,B,V] and so is its
     gradient; only the first derivative is available in that layout."""
     assert len(logits.shape) == 3
-    assert logits.dtype == torch.float32
+    # float32 like the reference (base_loss.py:131); bfloat16 logits are an extension (the kernels widen them on the fly,
+    # all arithmetic stays fp32, the gradient comes back in bfloat16; first derivative only)
+    assert logits.dtype in (torch.float32, torch.bfloat16)
     labels_t, ll_t, tl_t = torch.as_tensor(labels), torch.as_tensor(label_length), torch.as_tensor(logit_length)
     assert len(labels_t.shape) == 2 and len(ll_t.shape) == 1 and len(tl_t.shape) == 1
     assert logits.shape[1 if logits_time_major else 0] == labels_t.shape[0] == ll_t.shape[0] == tl_t.shape[0]
@@ -279,5 +283,6 @@ def ctc_loss(labels, logits, label_length, logit_length, blank_index, ctc_loss_d
     labels32, ll32, tl32 = _as_int32(labels_t, dev), _as_int32(ll_t, dev), _as_int32(tl_t, dev)
     U = _max_label_length_plus_one(ll_t, max_label_length, labels_t.shape[1])
     desc = _lib.make_desc(logits, labels32, _blank_to_int(blank_index), ctc_loss_data_cls._variant, U,
-                          _lib.TIME_MAJOR if logits_time_major else 0)
+                          (_lib.TIME_MAJOR if logits_time_major else 0) |
+                          (_lib.GRAD_BF16 if logits.dtype == torch.bfloat16 else 0))
     return _FusedLossFn.apply(logits, labels32, ll32, tl32, desc)

@@ -13,8 +13,10 @@ static int make_problem(const ctcb200_desc* d, Problem* p) {
   if (d->blank < 0 || d->blank >= d->V) return CTCB200_ERR_BAD_DESCRIPTOR;
   if (d->variant != CTCB200_CLASSIC && d->variant != CTCB200_SIMPLIFIED) return CTCB200_ERR_BAD_DESCRIPTOR;
   if (d->flags & ~(CTCB200_INPUT_LOGPROBAS | CTCB200_FORCE_STAGED | CTCB200_FORCE_FUSED | CTCB200_TIME_MAJOR |
-                   CTCB200_STAGE_MASK))
+                   CTCB200_LOGITS_BF16 | CTCB200_GRAD_BF16 | CTCB200_STAGE_MASK))
     return CTCB200_ERR_BAD_DESCRIPTOR;
+  if ((d->flags & CTCB200_GRAD_BF16) && !(d->flags & CTCB200_LOGITS_BF16)) return CTCB200_ERR_BAD_DESCRIPTOR;
+  if ((d->flags & CTCB200_LOGITS_BF16) && (d->flags & CTCB200_FORCE_STAGED)) return CTCB200_ERR_BAD_DESCRIPTOR;
   p->B = d->B; p->T = d->T; p->V = d->V; p->Lw = d->Lw; p->blank = d->blank; p->variant = d->variant;
   p->U = d->U > 0 ? d->U : d->Lw + 1;
   p->NS = (p->U + kWarp - 1) / kWarp;
@@ -23,6 +25,8 @@ static int make_problem(const ctcb200_desc* d, Problem* p) {
   p->Upad = p->NS * kWarp;
   p->S = d->variant == CTCB200_CLASSIC ? 2 : 1;
   p->input_logprobas = (d->flags & CTCB200_INPUT_LOGPROBAS) != 0;
+  p->logits_bf16 = (d->flags & CTCB200_LOGITS_BF16) != 0;
+  p->grad_bf16 = (d->flags & CTCB200_GRAD_BF16) != 0;
   const bool tm = (d->flags & CTCB200_TIME_MAJOR) != 0;
   p->stride_b = tm ? (size_t)d->V : (size_t)d->T * d->V;
   p->stride_t = tm ? (size_t)d->B * d->V : (size_t)d->V;
@@ -78,6 +82,7 @@ static size_t carve(const Problem& p, int what, bool fused_only, char* base, Scr
 // and the bases are 16-byte aligned, by 4-byte cp.async otherwise).
 static int fused_workers(const ctcb200_desc* desc, const Problem& p) {
   if (desc->flags & CTCB200_FORCE_STAGED) return 0;
+  if (p.logits_bf16) return fused_pick_workers(p);      // bf16 rows exist in the fused kernel only
   // Narrow vocabularies (character models, V < 64) in SMALL batches are latency-bound on the T-step chain rather than on
   // row traffic; there the staged recursion kernel, which streams the compact gathered rows, is faster (B=32 T=500 V=29:
   // 183 us staged vs 232 us fused).  From about 80 utterances on the fused kernel wins again because the staged gradient
@@ -140,7 +145,7 @@ const char* ctcb200_strerror(int code) {
     case CTCB200_ERR_NULL_POINTER: return "null pointer";
     case CTCB200_ERR_BAD_DESCRIPTOR: return "bad descriptor";
     case CTCB200_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
-    case CTCB200_ERR_UNSUPPORTED_SIZE: return "unsupported size (U > 512 states or V > 32768 tokens)";
+    case CTCB200_ERR_UNSUPPORTED_SIZE: return "unsupported size (U > 512 states, V > 32768 tokens, or bf16 rows the fused kernel cannot take)";
     case CTCB200_ERR_CUDA: return "CUDA launch failure";
     case CTCB200_ERR_MISALIGNED: return "workspace must be 256-byte aligned";
     default: return "unknown error";
@@ -188,6 +193,12 @@ int ctcb200_loss_grad(const ctcb200_desc* desc, const float* logits, const int32
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* loss_out = loss ? loss : s.loss;
   const int W = fused_workers(desc, p);
+  if (p.logits_bf16) {
+    // bf16 rows are a format of the fused kernel alone: TMA-movable rows (V % 8 == 0, 16-byte aligned bases), no
+    // log-probability gradient, and a shape the fused plan takes
+    const uintptr_t bases = reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(grad_logits);
+    if (grad_logprobas != nullptr || (p.V & 7) != 0 || (bases & 15) != 0 || W == 0 || p.T == 0) return CTCB200_ERR_UNSUPPORTED_SIZE;
+  }
   if (W > 0 && logits_only && p.T > 0) {
     CTCB200_CUDA(launch_fused(p, s, d_loss, loss_out, grad_logits, W, st));
     return CTCB200_OK;
@@ -206,7 +217,7 @@ int ctcb200_log_gradient(const ctcb200_desc* desc, const float* logits, const in
   int rc = check_common(desc, &p, CTCB200_WS_LOSS_GRAD, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, nullptr);
   if (rc != CTCB200_OK) return rc;
-  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
+  if (desc->flags & (CTCB200_TIME_MAJOR | CTCB200_LOGITS_BF16)) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (p.B == 0) return CTCB200_OK;
   if (log_gradient == nullptr && p.T > 0) return CTCB200_ERR_NULL_POINTER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -223,7 +234,7 @@ int ctcb200_states(const ctcb200_desc* desc, const float* logits, const int32_t*
   int rc = check_common(desc, &p, CTCB200_WS_STATES, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, nullptr);
   if (rc != CTCB200_OK) return rc;
-  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
+  if (desc->flags & (CTCB200_TIME_MAJOR | CTCB200_LOGITS_BF16)) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (desc->U <= 0) return CTCB200_ERR_BAD_DESCRIPTOR;   // the output shape depends on the true U
   if (p.B == 0) return CTCB200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -239,7 +250,7 @@ int ctcb200_gamma(const ctcb200_desc* desc, const float* logits, const int32_t* 
   int rc = check_common(desc, &p, CTCB200_WS_STATES, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, nullptr);
   if (rc != CTCB200_OK) return rc;
-  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
+  if (desc->flags & (CTCB200_TIME_MAJOR | CTCB200_LOGITS_BF16)) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (desc->U <= 0) return CTCB200_ERR_BAD_DESCRIPTOR;   // the output shape depends on the true U
   if (p.NS > 4) return CTCB200_ERR_UNSUPPORTED_SIZE;
   if (p.B == 0) return CTCB200_OK;
@@ -257,7 +268,7 @@ int ctcb200_hessian(const ctcb200_desc* desc, const float* logits, const int32_t
   int rc = check_common(desc, &p, CTCB200_WS_HESSIAN, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, &gtmp);
   if (rc != CTCB200_OK) return rc;
-  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
+  if (desc->flags & (CTCB200_TIME_MAJOR | CTCB200_LOGITS_BF16)) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (p.B == 0 || p.T == 0) return CTCB200_OK;
   if (hessian == nullptr) return CTCB200_ERR_NULL_POINTER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -277,7 +288,7 @@ int ctcb200_hvp(const ctcb200_desc* desc, const float* logits, const int32_t* la
   int rc = check_common(desc, &p, CTCB200_WS_HESSIAN, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, &gtmp);
   if (rc != CTCB200_OK) return rc;
-  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
+  if (desc->flags & (CTCB200_TIME_MAJOR | CTCB200_LOGITS_BF16)) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (p.B == 0 || p.T == 0) return CTCB200_OK;
   if (d_gradient == nullptr || out == nullptr) return CTCB200_ERR_NULL_POINTER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -296,7 +307,7 @@ int ctcb200_hvp_logits(const ctcb200_desc* desc, const float* logits, const int3
   int rc = check_common(desc, &p, CTCB200_WS_HVP_LOGITS, logits, labels, label_length, logit_length, workspace,
                         workspace_bytes, &s, &tmp);
   if (rc != CTCB200_OK) return rc;
-  if (desc->flags & CTCB200_TIME_MAJOR) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
+  if (desc->flags & (CTCB200_TIME_MAJOR | CTCB200_LOGITS_BF16)) return CTCB200_ERR_BAD_DESCRIPTOR;   // loss_grad only
   if (p.B == 0 || p.T == 0) return CTCB200_OK;
   if (v == nullptr || out == nullptr) return CTCB200_ERR_NULL_POINTER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -86,6 +86,7 @@ struct Problem {
   int Upad;   // 32 * NS
   int S;      // 1 simplified, 2 classic (closed/open)
   bool input_logprobas;
+  bool logits_bf16, grad_bf16;   // CTCB200_LOGITS_BF16 / CTCB200_GRAD_BF16: the fused kernel's bf16 row formats
   size_t stride_b, stride_t;   // floats between consecutive utterances / frames of logits and gradients (see row_offset)
   const float* logits;
   const int32_t* labels;

@@ -76,7 +76,7 @@ int ctcb200_host_create(const ctcb200_desc* desc, int device, int num_slices, ct
   for (int i = 0; i < num_slices && ok; ++i)
     ok = ok && cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaMalloc(&c->d_logits, n ? n * 4 : 256) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_logits, n ? n * 4 : 256) == cudaSuccess;     // (sized for fp32; bf16 rows use half of it)
   ok = ok && cudaMalloc(&c->d_grad, n ? n * 4 : 256) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_labels, (size_t)desc->B * desc->Lw * 4 + 256) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_label_length, (size_t)desc->B * 4 + 256) == cudaSuccess;
@@ -105,6 +105,12 @@ int ctcb200_host_loss_grad(ctcb200_host_ctx* c, const float* host_logits, const 
   if (cudaSetDevice(c->device) != cudaSuccess) return CTCB200_ERR_CUDA;
   const int slice_b = (d.B + c->num_slices - 1) / c->num_slices;
   const size_t tv = (size_t)d.T * d.V;
+  // element sizes of the logits / gradient rows: host and device buffers hold the same format (CTCB200_LOGITS_BF16 /
+  // CTCB200_GRAD_BF16), so bf16 logits halve the bytes that cross PCIe
+  const size_t es_in = (d.flags & CTCB200_LOGITS_BF16) ? 2 : 4, es_out = (d.flags & CTCB200_GRAD_BF16) ? 2 : 4;
+  const char* h_in = reinterpret_cast<const char*>(host_logits);
+  char* h_out = reinterpret_cast<char*>(host_grad_logits);
+  char *dv_in = reinterpret_cast<char*>(c->d_logits), *dv_out = reinterpret_cast<char*>(c->d_grad);
   int rc = CTCB200_OK;
   cudaStream_t copy = c->streams[0], run = c->streams[1], back = c->streams[2];
   for (int i = 0, b0 = 0; b0 < d.B; ++i, b0 += slice_b) {
@@ -112,21 +118,22 @@ int ctcb200_host_loss_grad(ctcb200_host_ctx* c, const float* host_logits, const 
     ctcb200_desc sd = d;
     sd.B = nb;
     bool ok = true;
-    if (tv) ok = ok && cudaMemcpyAsync(c->d_logits + b0 * tv, host_logits + b0 * tv, nb * tv * 4, cudaMemcpyHostToDevice, copy) == cudaSuccess;
+    if (tv) ok = ok && cudaMemcpyAsync(dv_in + b0 * tv * es_in, h_in + b0 * tv * es_in, nb * tv * es_in, cudaMemcpyHostToDevice, copy) == cudaSuccess;
     if (d.Lw) ok = ok && cudaMemcpyAsync(c->d_labels + (size_t)b0 * d.Lw, host_labels + (size_t)b0 * d.Lw, (size_t)nb * d.Lw * 4, cudaMemcpyHostToDevice, copy) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(c->d_label_length + b0, host_label_length + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, copy) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(c->d_logit_length + b0, host_logit_length + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, copy) == cudaSuccess;
     ok = ok && cudaEventRecord(c->landed[i], copy) == cudaSuccess;
     ok = ok && cudaStreamWaitEvent(run, c->landed[i], 0) == cudaSuccess;
     if (!ok) { rc = CTCB200_ERR_CUDA; break; }
-    rc = ctcb200_loss_grad(&sd, c->d_logits + b0 * tv, c->d_labels + (size_t)b0 * d.Lw, c->d_label_length + b0,
-                           c->d_logit_length + b0, nullptr, c->d_loss + b0, c->d_grad + b0 * tv, nullptr,
+    rc = ctcb200_loss_grad(&sd, reinterpret_cast<const float*>(dv_in + b0 * tv * es_in), c->d_labels + (size_t)b0 * d.Lw,
+                           c->d_label_length + b0, c->d_logit_length + b0, nullptr, c->d_loss + b0,
+                           reinterpret_cast<float*>(dv_out + b0 * tv * es_out), nullptr,
                            c->ws[0], c->ws_bytes, run);
     if (rc != CTCB200_OK) break;
     ok = cudaEventRecord(c->done[i], run) == cudaSuccess && cudaStreamWaitEvent(back, c->done[i], 0) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(host_loss + b0, c->d_loss + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, back) == cudaSuccess;
     if (host_grad_logits && tv)
-      ok = ok && cudaMemcpyAsync(host_grad_logits + b0 * tv, c->d_grad + b0 * tv, nb * tv * 4, cudaMemcpyDeviceToHost, back) == cudaSuccess;
+      ok = ok && cudaMemcpyAsync(h_out + b0 * tv * es_out, dv_out + b0 * tv * es_out, nb * tv * es_out, cudaMemcpyDeviceToHost, back) == cudaSuccess;
     if (!ok) { rc = CTCB200_ERR_CUDA; break; }
   }
   for (int i = 0; i < 3; ++i)

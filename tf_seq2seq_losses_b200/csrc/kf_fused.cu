@@ -4,9 +4,9 @@
 namespace ctcb200 {
 
 // Developer / test hook (ctcb200_debug_fused_plan in ctc_b200.h): a process-wide override of the plan below.
-static int g_plan_override[5] = {0, 0, 0, 0, 0};     // W, SL, XA, R, split; W == 0: no override
-void fused_set_plan_override(int W, int SL, int XA, int R, int split) {
-  const int v[5] = {W, SL, XA, R, split};
+static int g_plan_override[5] = {0, 0, 0, 0, 0};     // W, SL, XA, R, mode; W == 0: no override
+void fused_set_plan_override(int W, int SL, int XA, int R, int mode) {     // mode: bit 0 split, bit 1 no HALF scratch
+  const int v[5] = {W, SL, XA, R, mode};
   for (int i = 4; i >= 0; --i) __atomic_store_n(&g_plan_override[i], v[i], __ATOMIC_RELEASE);   // W last
 }
 
@@ -20,14 +20,25 @@ constexpr int kNumSms = 148;
 //   B <= 74  split: a cluster of two CTAs per utterance, one side each (W <= 8), every CTA with an SM to itself.  Needs
 //            TMA-movable rows (`tma_ok`).  Measured at T=1000 V=1024 L=200 (simplified): B=32 323 vs 427 us, B=64 323 vs
 //            431 us; two split CTAs sharing an SM (B=128) lose to the one-CTA plan, 640 vs 440 us.
-static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, int* R, int* split) {
-  *W = 0; *SL = 0; *XA = 0; *R = 0; *split = 0;
+// The HALF state scratch (fused_layout) is used whenever the plan allows it and its hand-over vectors fit the budget.
+static bool fits(const Problem& p, int W, int SL, int XA, int R, int sides, int budget, int want_half, int* half) {
+  for (int h = (want_half && fused_half_ok(p.S, W, R)) ? 1 : 0; h >= 0; --h)
+    if (fused_layout(p.V, p.Upad, p.S, W, SL, XA, R, sides, h).total <= budget) {
+      *half = h;
+      return true;
+    }
+  return false;
+}
+
+static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, int* R, int* split, int* half) {
+  *W = 0; *SL = 0; *XA = 0; *R = 0; *split = 0; *half = 0;
   if (p.NS > kMaxNS) return false;
   const int ow = __atomic_load_n(&g_plan_override[0], __ATOMIC_ACQUIRE);
+  const int mode = ow > 0 ? g_plan_override[4] : 0, want_half = (mode & 2) ? 0 : 1;
   if (ow > 0) {
-    const int sl = g_plan_override[1], xa = g_plan_override[2], r = g_plan_override[3], sp = g_plan_override[4] ? 1 : 0;
+    const int sl = g_plan_override[1], xa = g_plan_override[2], r = g_plan_override[3], sp = mode & 1;
     if (ow <= (sp ? kMaxWorkersSplit : kMaxWorkers) && sl >= 2 && sl <= 3 && xa >= 0 && xa <= 1 && r >= 1 && r <= 2 * ow &&
-        (!sp || tma_ok) && fused_layout(p.V, p.Upad, p.S, ow, sl, xa, r, sp ? 1 : 2).total <= kSmemPerSm) {
+        (!sp || tma_ok) && fits(p, ow, sl, xa, r, sp ? 1 : 2, kSmemPerSm, want_half, half)) {
       *W = ow; *SL = sl; *XA = xa; *R = r; *split = sp;
       return true;
     }
@@ -36,7 +47,7 @@ static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, 
     static const int scand[8][4] = {{8, 3, 1, 16}, {8, 2, 1, 16}, {8, 2, 0, 16}, {6, 3, 1, 12}, {6, 2, 1, 12}, {6, 2, 0, 12},
                                     {4, 3, 1, 8}, {4, 2, 0, 8}};
     for (int c = 0; c < 8; ++c)
-      if (fused_layout(p.V, p.Upad, p.S, scand[c][0], scand[c][1], scand[c][2], scand[c][3], 1).total <= kSmemPerSm) {
+      if (fits(p, scand[c][0], scand[c][1], scand[c][2], scand[c][3], 1, kSmemPerSm, want_half, half)) {
         *W = scand[c][0]; *SL = scand[c][1]; *XA = scand[c][2]; *R = scand[c][3]; *split = 1;
         return true;
       }
@@ -49,7 +60,7 @@ static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, 
   const int budgets[2] = {kSmemHalfSm, kSmemPerSm};
   for (int bi = 0; bi < 2; ++bi)
     for (int c = 0; c < 11; ++c) {
-      if (fused_layout(p.V, p.Upad, p.S, cand[c][0], cand[c][1], cand[c][2], cand[c][3]).total <= budgets[bi]) {
+      if (fits(p, cand[c][0], cand[c][1], cand[c][2], cand[c][3], 2, budgets[bi], want_half, half)) {
         *W = cand[c][0]; *SL = cand[c][1]; *XA = cand[c][2]; *R = cand[c][3];
         return true;
       }
@@ -58,8 +69,8 @@ static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, 
 }
 
 int fused_pick_workers(const Problem& p) {
-  int W, SL, XA, R, split;
-  fused_pick(p, false, &W, &SL, &XA, &R, &split);     // eligibility does not depend on the row mover
+  int W, SL, XA, R, split, half;
+  fused_pick(p, false, &W, &SL, &XA, &R, &split, &half);     // eligibility does not depend on the row mover
   return W;
 }
 
@@ -79,11 +90,13 @@ cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss
   a.dbg = reinterpret_cast<long long*>(s.betaT);   // the staged path's beta scratch is unused by the fused kernel
 #endif
   a.tma = ((p.V & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0) ? 1 : 0;
-  fused_pick(p, a.tma != 0, &a.W, &a.SL, &a.XA, &a.R, &a.split);
+  if (p.logits_bf16 && (!a.tma || (p.V & 7) != 0)) return cudaErrorInvalidValue;    // checked by the caller (api.cu)
+  fused_pick(p, a.tma != 0, &a.W, &a.SL, &a.XA, &a.R, &a.split, &a.half);
   (void)W;
   const bool classic = p.variant == CTCB200_CLASSIC;
-  if (classic) return a.tma ? launch_fused_variant<true, true>(a, st) : launch_fused_variant<true, false>(a, st);
-  return a.tma ? launch_fused_variant<false, true>(a, st) : launch_fused_variant<false, false>(a, st);
+  if (p.logits_bf16) return classic ? launch_fused_variant<true, true, true>(a, st) : launch_fused_variant<false, true, true>(a, st);
+  if (classic) return a.tma ? launch_fused_variant<true, true, false>(a, st) : launch_fused_variant<true, false, false>(a, st);
+  return a.tma ? launch_fused_variant<false, true, false>(a, st) : launch_fused_variant<false, false, false>(a, st);
 }
 
 }  // namespace ctcb200

@@ -42,6 +42,14 @@ constexpr int kFusedGroup = 4;      // frames per unrolled group (renormalisatio
 constexpr int kMaxWorkers = 4;       // workers per side when one CTA serves both sides of an utterance
 constexpr int kMaxWorkersSplit = 8;  // ... when each side has a CTA (and an SM, or half of one) to itself: see SPLIT below
 
+// A/B switches (developer builds, tools/build_variant.sh): the recursion warp's frame order, the wait watchdog
+#ifndef CTCB200_REC_REORDER
+#define CTCB200_REC_REORDER 1
+#endif
+#ifndef CTCB200_WATCHDOG
+#define CTCB200_WATCHDOG 1
+#endif
+
 // ---- PTX helpers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -75,13 +83,37 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {   // rele
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // try_wait suspends the warp in hardware until the phase completes or the time hint (ns) expires; the loop lives inside
-// the PTX block so a wake-up costs two instructions, and the long hint keeps idle warps off the issue slots.
+// the PTX block so a wake-up costs a few instructions, and the long hint keeps idle warps off the issue slots.
+// Watchdog: a wait that polls kWatchdogSpins times can only be a protocol bug (the longest legitimate wait is a few
+// microseconds of DRAM latency, a handful of polls; the limit is >= 0.1 s even if every poll returned at once): the kernel
+// traps -- a CUDA error the caller sees -- instead of hanging the GPU.
 #ifndef CTCB200_MBAR_HINT_NS
 #define CTCB200_MBAR_HINT_NS 20000
 #endif
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+constexpr unsigned kWatchdogSpins = 1u << 22;
+#ifdef CTCB200_WATCHDOG_VERBOSE
+// developer build: a C-level poll loop that says who is stuck where before it traps (`site` names the call site)
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity, int site = 0) {
+  for (unsigned n = 0;; ++n) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000) : "memory");
+    if (ok) break;
+    if (n == (1u << 15) && (threadIdx.x & 31) == 0)      // report, keep waiting so that every stuck warp gets to report ...
+      printf("libctc_b200 watchdog: block %d warp %d stuck at site %d, mbarrier +%u, parity %u\n", (int)blockIdx.x,
+             (int)(threadIdx.x >> 5), site, smem_u32(bar), parity);
+    if (n > (1u << 17)) __trap();                       // ... then give up
+  }
+  __syncwarp();
+}
+#else
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity, int site = 0) {
+  (void)site;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+#if CTCB200_WATCHDOG
+      ".reg .pred q;\n\t.reg .u32 n;\n\tmov.u32 n, 0;\n\t"
+#endif
       "CTCB200_WAIT:\n\t"
 #if CTCB200_MBAR_HINT_NS > 0
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
@@ -89,12 +121,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
 #endif
       "@p bra CTCB200_DONE;\n\t"
+#if CTCB200_WATCHDOG
+      "add.u32 n, n, 1;\n\tsetp.gt.u32 q, n, %3;\n\t@q trap;\n\t"
+#endif
       "bra CTCB200_WAIT;\n\t"
       "CTCB200_DONE:\n\t}"
       :
-      : "r"(smem_u32(bar)), "r"(parity), "r"(CTCB200_MBAR_HINT_NS)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(CTCB200_MBAR_HINT_NS), "r"(kWatchdogSpins)
       : "memory");
+#if CTCB200_WATCHDOG
+  // The trap is a second way out of the poll loop, and with it the compiler no longer re-converges the warp behind the
+  // loop on its own (measured: lanes ran on diverged and the row / ring hand-offs, written for converged warps, raced).
+  // Every call site is warp-uniform, so the warp is re-converged here explicitly.
+  __syncwarp();
+#endif
 }
+#endif
 // Optional L2 eviction priorities (-DCTCB200_L2_HINTS=1; off by default).  The kernel streams 3.1 GB of logits /
 // gradient rows through the 126 MB L2 exactly once per phase, while the 0.23 GB of stored recursion states are written
 // in phase A and read back last-in-first-out in phase B: with the hints rows are marked evict_first, states evict_last,
@@ -198,6 +240,19 @@ __device__ __forceinline__ float hsum4(float4 e) {
   return s.x + s.y;
 }
 
+// ---- bf16 rows (CTCB200_LOGITS_BF16): a row lands in the UPPER half of its fp32-sized buffer and is widened on the fly ----
+__device__ __forceinline__ float bf16_lo(unsigned w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(unsigned w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void widen8(uint4 q, float4& a, float4& b) {
+  a = make_float4(bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y));
+  b = make_float4(bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w));
+}
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {      // round to nearest even
+  unsigned r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // ---- optional wait-time instrumentation (compile with -DCTCB200_FUSED_TIMING; results go to FusedArgs::dbg) --------
 // per warp: [0] phase A cycles, [1] phase B cycles, [2] TMA wait, [3] dcount wait, [4] ccount wait, [5] scount wait,
 //           [6] done wait, [7] state cp.async wait; phase-B worker segments: [8] softmax pass, [9] occupancies,
@@ -219,11 +274,12 @@ __device__ __forceinline__ float hsum4(float4 e) {
 // ---- shared-memory layout (one definition for host sizing and device carving) ---------------------------------------
 struct FusedLayout {
   int W, R, SL, XA;         // workers per side, ring depth (W..2W), row buffers per worker, extra phase-A row buffers (0/1)
+  int half;                 // 1: phase A stores every second state row only, phase B derives the others (see HALF below)
   int off_xch, off_xoff, off_side0, total, xch_aliased;
   // offsets inside a side block
   int s_ctl, s_bar, s_row, s_aux, s_ringd, s_ringh, side_bytes;
   // offsets inside the aux block (phase B view)
-  int x_rings, x_ringc, x_stbuf;
+  int x_rings, x_ringc, x_stbuf, x_fwd;
 };
 
 __host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a * a; }
@@ -234,8 +290,16 @@ __host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a *
 // R = ring depth in frames (>= W; 2W unless shared memory is short).  The exchange vectors of the middle (S*Upad floats
 // per side, used only between the phases) alias each side's own input ring when that is large enough.
 // `sides` = 2 when one CTA holds both sides of the utterance, 1 in split mode (a CTA per side).
-__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL, int XA, int R, int sides = 2) {
+// HALF (simplified variant, even W and R): phase A writes the recursion state of every SECOND frame to global scratch.  In
+// phase B the worker of a frame whose row was stored (odd frames, counted from the middle) takes one recursion step from
+// it with the inputs of its own frame -- it holds them anyway -- and hands the result to the worker of the frame before
+// through shared memory (`fwd`, one vector per even ring slot, barrier fwd_full).  Halves the state traffic (0.40 ->
+// 0.20 GB at B=256 T=1000 U=201) and the global stores of the recursion warps.
+__host__ __device__ inline bool fused_half_ok(int S, int W, int R) { return S == 1 && (W & 1) == 0 && (R & 1) == 0; }
+__host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL, int XA, int R, int sides = 2,
+                                                    int half = 0) {
   FusedLayout f;
+  f.half = (half && fused_half_ok(S, W, R)) ? 1 : 0;
   f.W = W;
   f.R = R;
   f.SL = SL;
@@ -247,8 +311,10 @@ __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int 
   f.off_xoff = o; o += 2 * 8;
   o = fl_align(o, 128);
   int s = 0;
-  f.s_ctl = s;   s += 3 * f.R * 8;                            // ring barriers: full_d[R], full_s[R], empty[R]
-  f.s_bar = s;   s += W * kMaxRowSlots * 8;
+  // Two sets of every barrier, one per phase: all of them are initialised once at kernel start and none is ever
+  // re-initialised (see fused_body).
+  f.s_ctl = s;   s += 2 * 4 * f.R * 8;                        // ring barriers: full_d[R], full_s[R], empty[R], fwd_full[R]
+  f.s_bar = s;   s += 2 * W * kMaxRowSlots * 8;
   s = fl_align(s, 128);
   f.s_row = s;   s += W * SL * Vp * 4;
   int x = 0;
@@ -256,6 +322,7 @@ __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int 
   f.x_ringc = x; x += f.R * 8;
   x = fl_align(x, 16);
   f.x_stbuf = x; x += W * S * Upad * 4;
+  f.x_fwd = x;   x += f.half ? (f.R / 2) * Upad * 4 : 0;
   const int xa_bytes = XA * W * Vp * 4;
   f.s_aux = s;   s += fl_align(x > xa_bytes ? x : xa_bytes, 16);
   f.s_ringd = s; s += f.R * Upad * 4;
@@ -275,6 +342,7 @@ struct FusedArgs {
   float* loss;          // [B]
   float* grad;          // [B,T,V]
   int W, SL, XA, R;
+  int half;             // 1: HALF state scratch (see fused_layout)
   int split;            // 1: a cluster of two CTAs per utterance, one per side (small batches); 0: one CTA per utterance
   int tma;              // 1: rows move by 1-D TMA (V % 4 == 0, 16-byte aligned bases); 0: by 4-byte cp.async / plain stores
   long long* dbg;       // [B][warps][12] when built with CTCB200_FUSED_TIMING, else unused
@@ -288,6 +356,7 @@ struct SideView {
   unsigned long long* full_s;   // [R] recursion -> worker (phase B): the pre-step state of the frame is in the ring slot
   unsigned long long* empty;    // [R] slot released: by the recursion once it has read the inputs (phase A), by the
                                 //     worker once the frame's gradient row is finished (phase B)
+  unsigned long long* fwd_full; // [R] HALF: the derived other-side state of the (even) frame in this slot is in `fwd`
   unsigned long long* bar;   // [W][kMaxRowSlots]
   float* row;         // [W][SL][Vp]
   float* aux_rows;    // [W][Vp]  phase A only: one extra row buffer per worker (aliases rings / ringc / stbuf)
@@ -296,16 +365,18 @@ struct SideView {
   float* rings;       // [R][S*Upad]
   double* ringc;      // [R]
   float* stbuf;       // [W][S*Upad]
+  float* fwd;         // [R/2][Upad]  HALF only
 };
 
-__device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLayout& f, int side) {
+__device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLayout& f, int side, int phase) {
   unsigned char* base = smem + f.off_side0 + side * f.side_bytes;
   SideView v;
-  unsigned long long* ctl = reinterpret_cast<unsigned long long*>(base + f.s_ctl);
+  unsigned long long* ctl = reinterpret_cast<unsigned long long*>(base + f.s_ctl) + phase * (4 * f.R);
   v.full_d = ctl;
   v.full_s = ctl + f.R;
   v.empty = ctl + 2 * f.R;
-  v.bar = reinterpret_cast<unsigned long long*>(base + f.s_bar);
+  v.fwd_full = ctl + 3 * f.R;
+  v.bar = reinterpret_cast<unsigned long long*>(base + f.s_bar) + phase * (f.W * kMaxRowSlots);
   v.row = reinterpret_cast<float*>(base + f.s_row);
   v.aux_rows = reinterpret_cast<float*>(base + f.s_aux);
   v.ringd = reinterpret_cast<float*>(base + f.s_ringd);
@@ -313,6 +384,7 @@ __device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLa
   v.rings = reinterpret_cast<float*>(base + f.s_aux + f.x_rings);
   v.ringc = reinterpret_cast<double*>(base + f.s_aux + f.x_ringc);
   v.stbuf = reinterpret_cast<float*>(base + f.s_aux + f.x_stbuf);
+  v.fwd = reinterpret_cast<float*>(base + f.s_aux + f.x_fwd);
   return v;
 }
 
@@ -343,37 +415,43 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
   float* g_state = a.stateT + ((size_t)b * a.p.T + t_first) * (size_t)(S_ * kUpad);
   double* g_off = a.coff + (size_t)b * a.p.T + t_first;
   const ptrdiff_t g_step = (ptrdiff_t)t_step * (S_ * kUpad);
+  // Order inside a frame: the loads of the frame's inputs are issued first (their barrier was passed in the previous
+  // iteration), the publication of the pre-step state hides their latency, then the NEXT frame's barrier is awaited --
+  // its round trip is off the chain of the step that follows, whose result nobody needs before those inputs exist.
+#if CTCB200_REC_REORDER
+  if (count > 0) TIMED(3, mbar_wait(sv.full_d, 0u, 1));         // the first frame's inputs are in the ring
+#endif
 #pragma unroll 1
   for (int i = 0; i < count; ++i) {
-    TIMED(3, mbar_wait(sv.full_d + slot, use_par));          // the frame's inputs are in the ring
+#if !CTCB200_REC_REORDER
+    TIMED(3, mbar_wait(sv.full_d + slot, use_par, 1));
+#endif
     float d[NS];
     const float* dsrc = sv.ringd + slot * kUpad;
 #pragma unroll
     for (int j = 0; j < NS; ++j) d[j] = dsrc[j * kWarp + lane];
     const float h = sv.ringh[slot];
-    // What the other side / the row workers need of the pre-step state.  Simplified: the state.  Classic: from alpha
-    // the diagonal carrier x[l] = rep[l] ? A[l,0] : lse(A[l,0], A[l,1]) and the open plane A[l,1]; from beta the open
-    // plane B[l,1] alone (the blank's occupancy is the complement of the others, so B[l,0] is never read) -- the beta
-    // rows are half as wide, and no worker ever recomputes a log-sum-exp of the state.
     float S[NS], x[NS];
     if (CLASSIC && SIDE == 0) alpha_classic_prepare<NS>(v0, v1, lb, S, x);
     const float* out0 = !CLASSIC ? v0 : (SIDE == 0 ? x : v1);
     if (!phase_b) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sv.empty + slot);             // ring slot may be refilled
-      if (a.grad != nullptr) {      // (a loss-only call stops at the middle: nobody will read the scratch)
-        // -> global scratch for the other side's phase B
+      // -> global scratch for the other side's phase B, which walks these frames in reverse order (frame i here is its
+      // frame count-1-i): with HALF only its odd frames are stored.  A loss-only call stops at the middle: nobody will
+      // read the scratch.
+      if (a.grad != nullptr && (!f.half || ((count - 1 - i) & 1))) {
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
           stg_keep(g_state + j * kWarp + lane, out0[j]);
           if (CLASSIC && SIDE == 0) stg_keep(g_state + kUpad + j * kWarp + lane, v1[j]);
         }
         if (lane == 0) *g_off = c;
-        g_state += g_step;
-        g_off += t_step;
       }
+      g_state += g_step;
+      g_off += t_step;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sv.empty + slot);             // the inputs are in registers: the slot may be refilled
     } else {
-      if (i >= R) TIMED(6, mbar_wait(sv.empty + slot, use_par ^ 1u));   // previous frame of the slot is finished
+      if (i >= R) TIMED(6, mbar_wait(sv.empty + slot, use_par ^ 1u, 2));   // previous frame of the slot is finished
       float* dst = sv.rings + slot * (S_ * kUpad);
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
@@ -384,6 +462,11 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
       __syncwarp();
       if (lane == 0) mbar_arrive(sv.full_s + slot);
     }
+    const int nslot = (slot + 1 == R) ? 0 : slot + 1;
+    const unsigned npar = (nslot == 0) ? (use_par ^ 1u) : use_par;
+#if CTCB200_REC_REORDER
+    if (i + 1 < count) TIMED(3, mbar_wait(sv.full_d + nslot, npar, 1));     // the next frame's inputs are in the ring
+#endif
     if (SIDE == 0) {
       if (CLASSIC) alpha_classic_finish<NS>(v0, v1, S, x, d, h, lane, lb);
       else alpha_step_simplified<NS>(v0, d, h, lane);
@@ -395,7 +478,8 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
     const int k = i & (kFusedGroup - 1);
     if (k == 0) m_pend = state_max<NS, CLASSIC>(v0, v1);
     else if (k == 2) apply_offset<NS, CLASSIC>(v0, v1, m_pend, c);
-    if (++slot == R) { slot = 0; use_par ^= 1u; }
+    slot = nslot;
+    use_par = npar;
   }
 }
 
@@ -421,7 +505,7 @@ struct LaneLabels {
 // tok[j] = cleaned label (base_loss.py:395-418) of this lane's states l = lane*NS + j (always a safe column index);
 // `ll` holds their static facts (LaneLabels).  `side` is a runtime argument (one code body for both sides keeps the
 // instruction footprint inside the instruction cache).
-template <int NS, bool CLASSIC, bool PHASE_B, bool TMA>
+template <int NS, bool CLASSIC, bool PHASE_B, bool TMA, bool BF16>
 __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int side, int b,
                                           int w, int count, int t_first, int t_step, int L, double lossd_mid, float dl,
                                           const int (&tok)[NS], const LaneLabels ll, int lane, long long* tm) {
@@ -431,9 +515,12 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   const int W = f.W, R = f.R, V = p.V, Vp = (V + 3) & ~3, n4 = Vp >> 2;
   const int SL = PHASE_B ? f.SL : f.SL + f.XA;      // phase A may own one more row buffer (see fused_layout)
   const int n_my = (count > w) ? (count - w + W - 1) / W : 0;
-  const unsigned row_bytes = (unsigned)V * 4u;
+  static_assert(!BF16 || TMA, "bf16 rows move by TMA only");
+  const unsigned row_bytes = (unsigned)V * 4u, in_bytes = BF16 ? (unsigned)V * 2u : row_bytes;
   constexpr bool tma = TMA;
-  const float* logits_b = p.logits + row_offset(p, b, 0);
+  const int n8 = V >> 3;                               // bf16 rows: 16-byte groups of eight (V % 8 == 0)
+  const float* logits_b = p.logits + row_offset(p, b, 0);                                       // fp32 rows
+  const char* logits_hb = reinterpret_cast<const char*>(p.logits) + 2 * row_offset(p, b, 0);    // bf16 rows
   float* rowbuf = sv.row + (size_t)w * f.SL * Vp;
   float* rowx = sv.aux_rows + (size_t)w * Vp;
   auto slot_ptr = [&](int q) { return (q < f.SL) ? rowbuf + (size_t)q * Vp : rowx; };
@@ -445,8 +532,9 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     if (tma) {
       if (lane == 0) {
         fence_proxy_async();
-        mbar_expect_tx(bars_of(sv, w) + q, row_bytes);
-        bulk_load(dst, src, row_bytes, bars_of(sv, w) + q);
+        mbar_expect_tx(bars_of(sv, w) + q, in_bytes);
+        if (BF16) bulk_load(dst + (Vp >> 1), logits_hb + 2 * (size_t)t * p.stride_t, in_bytes, bars_of(sv, w) + q);
+        else bulk_load(dst, src, row_bytes, bars_of(sv, w) + q);
       }
     } else {
       for (int k = lane; k < V; k += kWarp) fused_cp_async4(dst + k, src + k);
@@ -467,13 +555,33 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   unsigned use_par = 0;    // (i / R) & 1
   int rs = 0;              // row buffer of row n (= n % SL)
   unsigned par = 0;        // bit q: parity of the next completion to wait for on row buffer q
-  // scalars of the row produced in phase A, fetched one row ahead (plain loads: written by this CTA in phase A)
+  // HALF (see fused_layout): only the rows of odd frames (counted from the middle) were stored.  W is even, so a worker
+  // sees frames of one parity: odd workers read stored rows -- fetched a whole iteration ahead -- and derive the state of
+  // the frame before; even workers receive that through `fwd` and never touch the global scratch.
+  const bool half = PHASE_B && !CLASSIC && f.half;
+  const bool odd_w = half && (w & 1), even_w = half && !(w & 1);
+  // the other side's stored state of frame `tt`: async copy into this worker's staging buffer
+  auto fetch_state = [&](int tt) {
+    const float* src = a.stateT + ((size_t)b * p.T + tt) * (size_t)(S * kUpad);
+    const int n16 = ((CLASSIC && side == 0) ? 1 : S) * (kUpad / 4);      // classic beta rows hold the open plane only
+#pragma unroll
+    for (int k = 0; k < (S * kUpad / 4 + kWarp - 1) / kWarp; ++k) {
+      const int cidx = k * kWarp + lane;
+      if (cidx < n16) fused_cp_async16_keep(stb + 4 * cidx, src + 4 * cidx);
+    }
+    fused_cp_async_commit();
+  };
+  // scalars of the row produced in phase A, fetched one row ahead (plain loads: written by this CTA in phase A).  The
+  // offset of a derived state is that of the stored row it was derived from (the next frame's); the last frame of an
+  // odd-length phase has no such row: its other-side state is the initial vector, offset 0.
   float lse_next = 0.0f;
   double cst_next = 0.0;
   if (PHASE_B && n_my > 0) {
     const int t0 = t_first + w * t_step;
     if (!p.input_logprobas) lse_next = rowlse_b[t0];
-    cst_next = coff_b[t0];
+    if (!even_w) cst_next = coff_b[t0];
+    else if (w + 1 < count) cst_next = coff_b[t0 + t_step];
+    if (odd_w) fetch_state(t0);
   }
   for (int n = 0; n < n_my; ++n) {
     const int i = w + n * W;
@@ -481,27 +589,23 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     float lse = lse_next;
     const double cst = cst_next;
     if (PHASE_B) {
-      // the other side's stored state for this frame: async copy now, consumed after the recursion catches up
-      const float* src = a.stateT + ((size_t)b * p.T + t) * (size_t)(S * kUpad);
-      const int n16 = ((CLASSIC && side == 0) ? 1 : S) * (kUpad / 4);      // classic beta rows hold the open plane only
-#pragma unroll
-      for (int k = 0; k < (S * kUpad / 4 + kWarp - 1) / kWarp; ++k) {
-        const int cidx = k * kWarp + lane;
-        if (cidx < n16) fused_cp_async16_keep(stb + 4 * cidx, src + 4 * cidx);
-      }
-      fused_cp_async_commit();
+      if (!half) fetch_state(t);     // consumed after the recursion catches up
       if (n + 1 < n_my) {
         const int tn = t + W * t_step;
         if (!p.input_logprobas) lse_next = rowlse_b[tn];
-        cst_next = coff_b[tn];
+        if (!even_w) cst_next = coff_b[tn];
+        else cst_next = (i + W + 1 < count) ? coff_b[tn + t_step] : 0.0;
       }
     }
     // ---- prefetch (phase A): the buffer row n-1 used is free as soon as this iteration starts ----
     if (!PHASE_B && n + SL - 1 < n_my) load_row((rs == 0) ? SL - 1 : rs - 1, t + (SL - 1) * W * t_step);
-    TIMED(2, mbar_wait(bars + rs, (par >> rs) & 1u));          // the row has landed
+    TIMED(2, mbar_wait(bars + rs, (par >> rs) & 1u, 3));          // the row has landed
     par ^= 1u << rs;
     float* row = slot_ptr(rs);
     float4* row4 = reinterpret_cast<float4*>(row);
+    const uint4* rowh = reinterpret_cast<const uint4*>(row + (Vp >> 1));                  // bf16 row: upper half of the buffer
+    const unsigned short* rowh16 = reinterpret_cast<const unsigned short*>(row + (Vp >> 1));
+    auto in_at = [&](int k) { return BF16 ? __uint_as_float((unsigned)rowh16[k] << 16) : row[k]; };   // raw input element k
 
     // ---- stage 1: row log-sum-exp (phase A; one pass, the row chunk lives in registers) and the label gather ----
 #ifdef CTCB200_FUSED_TIMING
@@ -509,7 +613,13 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 #endif
     if (!PHASE_B && !p.input_logprobas) {
       float m_run = kNegInf, s_run = 0.0f;
-      if (n4 <= kWarp) {   // narrow rows (V <= 128): one float4 per lane
+      if (BF16 && n4 <= kWarp) {   // narrow bf16 rows (V <= 128): one group of eight per lane
+        float4 v0 = make_float4(kNegInf, kNegInf, kNegInf, kNegInf), v1 = v0;
+        if (lane < n8) widen8(rowh[lane], v0, v1);
+        m_run = fmaxf(fmaxf(fmaxf(v0.x, v0.y), fmaxf(v0.z, v0.w)), fmaxf(fmaxf(v1.x, v1.y), fmaxf(v1.z, v1.w)));
+        const float mn0 = (m_run == kNegInf || m_run == INFINITY) ? 0.0f : m_run;
+        s_run = hsum4(exp4_shifted(v0, mn0)) + hsum4(exp4_shifted(v1, mn0));
+      } else if (n4 <= kWarp) {   // narrow rows (V <= 128): one float4 per lane
         const float4 v = (lane < n4) ? row4[lane] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
         m_run = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
         const float mn0 = (m_run == kNegInf || m_run == INFINITY) ? 0.0f : m_run;
@@ -519,10 +629,19 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
         auto chunk = [&](auto checked, int base) {
           constexpr bool kChecked = decltype(checked)::value;
           float4 v[8];
+          if (BF16) {      // the same 1024 elements as four groups of eight per lane
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int c4 = base + u * kWarp + lane;
-            v[u] = (!kChecked || c4 < n4) ? row4[c4] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+            for (int u = 0; u < 4; ++u) {
+              const int g = (base >> 1) + u * kWarp + lane;
+              v[2 * u] = v[2 * u + 1] = make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+              if (!kChecked || g < n8) widen8(rowh[g], v[2 * u], v[2 * u + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int c4 = base + u * kWarp + lane;
+              v[u] = (!kChecked || c4 < n4) ? row4[c4] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+            }
           }
           float pm[8];
 #pragma unroll
@@ -553,23 +672,43 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     tm[6] += clock64() - t_s0;   // workers: row statistics
     const long long t_g0 = clock64();
 #endif
-    if (!PHASE_B && i >= R) TIMED(4, mbar_wait(sv.empty + slot, use_par ^ 1u));   // slot consumed by the recursion
+    if (!PHASE_B && i >= R) TIMED(4, mbar_wait(sv.empty + slot, use_par ^ 1u, 4));   // slot consumed by the recursion
     float dd[NS];
     {
       float* dst = sv.ringd + slot * kUpad;
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        dd[j] = ll.ok(j) ? row[tok[j]] - lse : kNegInf;
+        dd[j] = ll.ok(j) ? in_at(tok[j]) - lse : kNegInf;
         dst[j * kWarp + lane] = dd[j];
       }
     }
-    const float h = row[p.blank] - lse;
+    const float h = in_at(p.blank) - lse;
     if (lane == 0) sv.ringh[slot] = h;
     __syncwarp();
     if (lane == 0) mbar_arrive(sv.full_d + slot);
 #ifdef CTCB200_FUSED_TIMING
     tm[3] += clock64() - t_g0;   // workers: ring wait + gather + publish
 #endif
+
+    // ---- HALF, odd frames: one recursion step from the stored state with this frame's inputs gives the other side's
+    // state of the frame before (beta[t] from beta[t+1] on the alpha side, alpha[t+1] from alpha[t] on the beta side).
+    if (odd_w) {
+      TIMED(7, fused_cp_async_wait_all());
+      __syncwarp();
+      const int sp = slot ? slot - 1 : R - 1;                       // ring slot of frame i-1
+      const unsigned pp = slot ? use_par : use_par ^ 1u;            // parity of that use of it
+      if (i - 1 >= R) mbar_wait(sv.empty + sp, pp ^ 1u, 7);            // the previous user of its fwd vector (frame i-1-R) is done
+      float st[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) st[j] = stb[j * kWarp + lane];
+      if (side == 0) beta_step_simplified<NS>(st, dd, h, lane);
+      else alpha_step_simplified<NS>(st, dd, h, lane);
+      float* fw = sv.fwd + (sp >> 1) * kUpad;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) fw[j * kWarp + lane] = st[j];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sv.fwd_full + sp);
+    }
 
     // ---- stage 1b (phase B): the dense softmax part of the gradient row, in place, while the recursion catches up.
     // d loss/d logit = d_loss * (softmax * sum_k occ - occ); sum_k occ is 1 for every frame of a feasible sample (it is
@@ -591,17 +730,48 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           }
           return e;
         };
-        int c4 = lane;
-        for (; c4 + 3 * kWarp < n4; c4 += 4 * kWarp) {
-          float4 v[4];
+        if (BF16) {
+          // Widening in place: group g (eight bf16 in the upper half) becomes float4 2g, 2g+1 of the lower part.  Elements
+          // are taken in increasing order, every batch loads before it stores, and the fp32 image of elements < e ends at
+          // byte 4e <= 2V + 2e, where the unread bf16 data begins: a batch can only overwrite what it has already read.
+          int g = lane;
+          for (; (g - lane) + 2 * kWarp <= n8; g += 2 * kWarp) {      // full batches: warp-uniform trip count
+            const uint4 q0 = rowh[g], q1 = rowh[g + kWarp];
+            float4 v[4];
+            widen8(q0, v[0], v[1]);
+            widen8(q1, v[2], v[3]);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = row4[c4 + u * kWarp];
+            for (int u = 0; u < 4; ++u) v[u] = fin(v[u]);
+            __syncwarp();
+            row4[2 * g] = v[0];
+            row4[2 * g + 1] = v[1];
+            row4[2 * (g + kWarp)] = v[2];
+            row4[2 * (g + kWarp) + 1] = v[3];
+            __syncwarp();
+          }
+          for (; g - lane < n8; g += kWarp) {      // warp-uniform trip count (the barriers inside need every lane)
+            float4 v0, v1;
+            if (g < n8) widen8(rowh[g], v0, v1);
+            __syncwarp();
+            if (g < n8) {
+              row4[2 * g] = fin(v0);
+              row4[2 * g + 1] = fin(v1);
+            }
+            __syncwarp();
+          }
+        } else {
+          int c4 = lane;
+          for (; c4 + 3 * kWarp < n4; c4 += 4 * kWarp) {
+            float4 v[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = fin(v[u]);
+            for (int u = 0; u < 4; ++u) v[u] = row4[c4 + u * kWarp];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) row4[c4 + u * kWarp] = v[u];
+            for (int u = 0; u < 4; ++u) v[u] = fin(v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) row4[c4 + u * kWarp] = v[u];
+          }
+          for (; c4 < n4; c4 += kWarp) row4[c4] = fin(row4[c4]);
         }
-        for (; c4 < n4; c4 += kWarp) row4[c4] = fin(row4[c4]);
       };
       if (dl == 1.0f) softmax_in_place(std::false_type{});     // no upstream gradient (or ones): skip the scaling
       else softmax_in_place(std::true_type{});
@@ -619,21 +789,37 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 
     // ---- stage 2 (phase B): occupancies of the frame, scattered into the row; then the row leaves by TMA ----
     if (PHASE_B) {
-      TIMED(5, mbar_wait(sv.full_s + slot, use_par));          // the running side's state for this frame is published
-      TIMED(7, fused_cp_async_wait_all());
-      __syncwarp();
-      {   // the stored state row is dead now: drop it from L2 instead of letting it be written back (rows are 128-byte
-          // multiples at 128-byte aligned offsets of the workspace)
+      TIMED(5, mbar_wait(sv.full_s + slot, use_par, 5));          // the running side's state for this frame is published
+      const float* other = stb;                                  // the other side's state for this frame
+      if (!even_w) {
+        TIMED(7, fused_cp_async_wait_all());
+        __syncwarp();
+        // the stored state row is dead now: drop it from L2 instead of letting it be written back (rows are 128-byte
+        // multiples at 128-byte aligned offsets of the workspace)
         const char* dead_row = reinterpret_cast<const char*>(a.stateT + ((size_t)b * p.T + t) * (size_t)(S * kUpad));
         if (lane < S * kUpad * 4 / 128) l2_discard128(dead_row + lane * 128);
+      } else {
+        float* fw = sv.fwd + (slot >> 1) * kUpad;
+        __syncwarp();                                              // (every lane is past its part of the softmax pass)
+        if (i + 1 < count) {
+          TIMED(7, mbar_wait(sv.fwd_full + slot, use_par, 6));      // derived by the worker of frame i+1
+        } else {
+          // last frame of an odd-length phase: the other side's INITIAL vector (beta[n] = one-hot(label_length) on the
+          // alpha side, alpha[0] = one-hot(0) on the beta side)
+          if (i >= R) mbar_wait(sv.empty + slot, use_par ^ 1u, 8);
+#pragma unroll
+          for (int j = 0; j < NS; ++j) fw[j * kWarp + lane] = (lane * NS + j == (side == 0 ? L : 0)) ? 0.0f : kNegInf;
+          __syncwarp();
+        }
+        other = fw;
       }
 #ifdef CTCB200_FUSED_TIMING
       const long long t_o0 = clock64();
 #endif
       const float* ring_state = sv.rings + slot * (S * kUpad);
       const float K = (float)(lossd_mid + sv.ringc[slot] + cst);   // loss + both renormalisation offsets
-      const float* A = (side == 0) ? ring_state : stb;         // alpha[t]
-      const float* Bn = (side == 0) ? stb : ring_state;        // beta[t+1]
+      const float* A = (side == 0) ? ring_state : other;       // alpha[t]
+      const float* Bn = (side == 0) ? other : ring_state;      // beta[t+1]
       float occ[NS], occ_stay[NS];
       if (!CLASSIC) {
         float a0[NS], b0[NS];
@@ -641,6 +827,10 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
         for (int j = 0; j < NS; ++j) {
           a0[j] = A[j * kWarp + lane];
           b0[j] = Bn[j * kWarp + lane];
+        }
+        if (odd_w && n + 1 < n_my) {      // the staging buffer is in registers now: fetch this worker's next stored row
+          __syncwarp();
+          fetch_state(t + W * t_step);
         }
         float bx = __shfl_down_sync(kFull, b0[0], 1);
         if (lane == 31) bx = kNegInf;
@@ -726,7 +916,21 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       if (lane == 0) row[p.blank] -= dl * occ_blank;
       __syncwarp();
       float* gdst = a.grad + row_offset(p, b, t);
-      if (tma) {
+      if (BF16 && p.grad_bf16) {
+        // narrow the finished row in place (element k -> bytes 2k..2k+1: again only already-read bytes are overwritten)
+        uint4* out8 = reinterpret_cast<uint4*>(row);
+        for (int g = lane; g - lane < n8; g += kWarp) {
+          float4 v0, v1;
+          if (g < n8) { v0 = row4[2 * g]; v1 = row4[2 * g + 1]; }
+          __syncwarp();
+          if (g < n8) out8[g] = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+          __syncwarp();
+        }
+        if (lane == 0) {
+          fence_proxy_async();
+          bulk_store(reinterpret_cast<char*>(a.grad) + 2 * row_offset(p, b, t), row, in_bytes);
+        }
+      } else if (tma) {
         if (lane == 0) {
           fence_proxy_async();                                  // generic-proxy writes -> visible to the TMA store
           bulk_store(gdst, row, row_bytes);
@@ -755,12 +959,12 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 //                is the runtime.  Every side gets twice the row workers, its own shared memory and a less crowded
 //                scheduler; the sides only talk at the middle (state vectors through distributed shared memory, two cluster
 //                barriers) and through the global scratch the other side reads back in phase B.
-template <int NS, bool CLASSIC, bool TMA, bool SPLIT>
+template <int NS, bool CLASSIC, bool TMA, bool SPLIT, bool BF16>
 __device__ __forceinline__ void fused_body(const FusedArgs& a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const Problem& p = a.p;
-  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA, a.R, SPLIT ? 1 : 2);
+  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA, a.R, SPLIT ? 1 : 2, a.half);
   const int b = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = f.W;
   // Warp -> (side, role); role 0 = recursion warp, 1..W = row workers.  Other placements were measured on B200 (the two
@@ -777,18 +981,20 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
     return reinterpret_cast<float*>(smem + (f.xch_aliased ? f.off_side0 + s2 * f.side_bytes + f.s_ringd : f.off_xch + s2 * (S * kUpad * 4)));
   };
   double* xoff = reinterpret_cast<double*>(smem + f.off_xoff);
-  const SideView sv = side_view(smem, f, my);
 
-  auto reset_sync_state = [&]() {     // one thread: counters to zero, mbarriers to phase 0
+  // Every mbarrier is initialised exactly once, here, long before its first use; each phase has its own set.  (Round 2
+  // found that RE-initialising the barriers at the middle is fragile: depending on register allocation the compiler
+  // emitted the side-0 mbarrier.init as a plain 64-bit shared store, and arrivals of phase B that followed the closing
+  // __syncthreads were lost on exactly those barriers -- wrong recursion inputs on short utterances, a deadlock on long
+  // ones.  With one set per phase nothing is ever re-initialised while the kernel runs.)
+  if (tid == 0) {
     for (int s2 = 0; s2 < (SPLIT ? 1 : 2); ++s2) {
-      const SideView v = side_view(smem, f, s2);
-      for (int k = 0; k < 3 * f.R; ++k) mbar_init(v.full_d + k, 1u);
-      for (int k = 0; k < W * kMaxRowSlots; ++k) mbar_init(v.bar + k, TMA ? 1u : (unsigned)kWarp);
+      const SideView v = side_view(smem, f, s2, 0);      // the two sets are contiguous
+      for (int k = 0; k < 2 * 4 * f.R; ++k) mbar_init(v.full_d + k, 1u);
+      for (int k = 0; k < 2 * W * kMaxRowSlots; ++k) mbar_init(v.bar + k, TMA ? 1u : (unsigned)kWarp);
     }
     fence_mbar_init();
-  };
-
-  if (tid == 0) reset_sync_state();
+  }
   __syncthreads();
 
   // this lane's labels and their static facts, in registers for the whole kernel (see LaneLabels)
@@ -856,13 +1062,14 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
       tf = (side == 0) ? M : M - 1;
     }
     const int ts = (side == 0) ? 1 : -1;
+    const SideView sv = side_view(smem, f, my, ph);      // this phase's barrier set
     if (role == 0) {
       if (side == 0) rec_phase<NS, CLASSIC, 0>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
       else rec_phase<NS, CLASSIC, 1>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
     } else if (ph == 0) {
-      worker_phase<NS, CLASSIC, false, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, ll, lane, tm);
+      worker_phase<NS, CLASSIC, false, TMA, BF16>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, ll, lane, tm);
     } else {
-      worker_phase<NS, CLASSIC, true, TMA>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, ll, lane, tm);
+      worker_phase<NS, CLASSIC, true, TMA, BF16>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, ll, lane, tm);
     }
     if (ph == 1) break;
 #ifdef CTCB200_FUSED_TIMING
@@ -885,7 +1092,6 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
     double off_sum;
     if (!SPLIT) {
       __syncthreads();     // also makes phase A's global scratch visible to the whole CTA
-      if (tid == 0) reset_sync_state();
       const float *xa = xch_of(0), *xb = xch_of(1);
       for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(xa[q] + xb[q]);
       off_sum = xoff[0] + xoff[1];
@@ -894,7 +1100,6 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
       // memory.  The cluster barrier (release / acquire) also publishes phase A's global scratch -- row log-sum-exps,
       // stored states, offsets -- to the peer, which reads it back in phase B.
       cluster_sync_all();
-      if (tid == 0) reset_sync_state();
       const float* own = xch_of(0);
       const unsigned peer = cluster_map(smem_u32(own), (unsigned)(side ^ 1));
       for (int q = lane; q < S * kUpad; q += kWarp) zacc.add(own[q] + ld_dsmem_f32(peer + 4u * q));
@@ -933,25 +1138,30 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
   }
   if (role > 0) {     // frames beyond logit_length, or every frame of an infeasible sample: exact zeros
     const int widx = side * W + (role - 1);
-    for (int r = (dead ? 0 : n_t) + widx; r < p.T; r += 2 * W) fused_zero_row(a.grad + row_offset(p, b, r), p.V, lane, TMA);
+    for (int r = (dead ? 0 : n_t) + widx; r < p.T; r += 2 * W) {
+      if (BF16 && p.grad_bf16)       // a bf16 row is V/2 floats wide (V % 8 == 0)
+        fused_zero_row(reinterpret_cast<float*>(reinterpret_cast<char*>(a.grad) + 2 * row_offset(p, b, r)), p.V >> 1, lane, true);
+      else
+        fused_zero_row(a.grad + row_offset(p, b, r), p.V, lane, TMA);
+    }
   }
 }
 
 // ---- the two kernels ----------------------------------------------------------------------------------------------------
-template <int NS, bool CLASSIC, bool TMA>
+template <int NS, bool CLASSIC, bool TMA, bool BF16>
 __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
-  fused_body<NS, CLASSIC, TMA, false>(a);
+  fused_body<NS, CLASSIC, TMA, false, BF16>(a);
 }
-template <int NS, bool CLASSIC, bool TMA>
+template <int NS, bool CLASSIC, bool TMA, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__((NS <= 8) ? 112 : 224)
     kf_fused_split(const __grid_constant__ FusedArgs a) {
-  fused_body<NS, CLASSIC, TMA, true>(a);
+  fused_body<NS, CLASSIC, TMA, true, BF16>(a);
 }
 
 // ---- host side: one launcher per (variant, row-mover) pair, defined in kf_fused_*.cu --------------------------------
 constexpr int kSmemPerSm = 227 * 1024;
 
-template <bool CLASSIC, bool TMA>
+template <bool CLASSIC, bool TMA, bool BF16>
 cudaError_t launch_fused_variant(const FusedArgs& a, cudaStream_t st);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is issued once per (kernel, device) -- or again when a later problem
@@ -972,65 +1182,57 @@ static cudaError_t ensure_smem(Kernel kernel, int* cache, int bytes) {
   return e;
 }
 
-template <int NS, bool CLASSIC, bool TMA>
+template <int NS, bool CLASSIC, bool TMA, bool BF16>
 static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
-  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA, a.R, a.split ? 1 : 2);
+  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA, a.R, a.split ? 1 : 2, a.half);
   // NOTE: a concurrent caller on the same device may raise the attribute between this check and the launch; it is
   // never lowered, so the launch below always finds at least f.total bytes allowed.
   static int cache[2][kMaxDevices];
   if (a.split) {
     if constexpr (TMA) {       // the split plan exists for TMA-movable rows only (fused_pick never asks for it otherwise)
-      cudaError_t e = ensure_smem(kf_fused_split<NS, CLASSIC, TMA>, cache[1], f.total);
+      cudaError_t e = ensure_smem(kf_fused_split<NS, CLASSIC, TMA, BF16>, cache[1], f.total);
       if (e != cudaSuccess) return e;
-      kf_fused_split<NS, CLASSIC, TMA><<<2 * a.p.B, (a.W + 1) * kWarp, f.total, st>>>(a);
+      kf_fused_split<NS, CLASSIC, TMA, BF16><<<2 * a.p.B, (a.W + 1) * kWarp, f.total, st>>>(a);
     } else {
       return cudaErrorInvalidValue;
     }
   } else {
-    cudaError_t e = ensure_smem(kf_fused<NS, CLASSIC, TMA>, cache[0], f.total);
+    cudaError_t e = ensure_smem(kf_fused<NS, CLASSIC, TMA, BF16>, cache[0], f.total);
     if (e != cudaSuccess) return e;
-    kf_fused<NS, CLASSIC, TMA><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
+    kf_fused<NS, CLASSIC, TMA, BF16><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
   }
   const cudaError_t err = cudaGetLastError();
   if (err == cudaErrorLaunchOutOfResources) {      // say which resource: the plan and the compiled kernel disagree
     cudaFuncAttributes fa{};
     if constexpr (TMA) {
-      if (a.split) (void)cudaFuncGetAttributes(&fa, kf_fused_split<NS, CLASSIC, TMA>);
-      else (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA>);
+      if (a.split) (void)cudaFuncGetAttributes(&fa, kf_fused_split<NS, CLASSIC, TMA, BF16>);
+      else (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA, BF16>);
     } else {
-      (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA>);
+      (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA, BF16>);
     }
-    fprintf(stderr, "libctc_b200: kf_fused%s<NS=%d,classic=%d,tma=%d> W=%d SL=%d XA=%d R=%d: %d threads, %d B dynamic smem; kernel: %d regs, "
+    fprintf(stderr, "libctc_b200: kf_fused%s<NS=%d,classic=%d,tma=%d> bf16=%d W=%d SL=%d XA=%d R=%d: %d threads, %d B dynamic smem; kernel: %d regs, "
             "max %d threads/block, %zu B static smem, %d B max dynamic smem, %zu B local\n", a.split ? "_split" : "", NS, (int)CLASSIC,
-            (int)TMA, a.W, a.SL, a.XA, a.R, (a.split ? 1 : 2) * (a.W + 1) * kWarp, f.total, fa.numRegs, fa.maxThreadsPerBlock,
+            (int)TMA, (int)BF16, a.W, a.SL, a.XA, a.R, (a.split ? 1 : 2) * (a.W + 1) * kWarp, f.total, fa.numRegs, fa.maxThreadsPerBlock,
             fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes);
     (void)cudaGetLastError();
   }
   return err;
 }
 
-#define CTCB200_DEFINE_FUSED_VARIANT(CLASSIC_, TMA_)                                                        \
-  template <>                                                                                               \
-  cudaError_t launch_fused_variant<CLASSIC_, TMA_>(const FusedArgs& a, cudaStream_t st) {                   \
-    switch (a.p.NS) {                                                                                       \
-      case 1: return launch_fused_ns<1, CLASSIC_, TMA_>(a, st);                                             \
-      case 2: return launch_fused_ns<2, CLASSIC_, TMA_>(a, st);                                             \
-      case 3: return launch_fused_ns<3, CLASSIC_, TMA_>(a, st);                                             \
-      case 4: return launch_fused_ns<4, CLASSIC_, TMA_>(a, st);                                             \
-      case 5: return launch_fused_ns<5, CLASSIC_, TMA_>(a, st);                                             \
-      case 6: return launch_fused_ns<6, CLASSIC_, TMA_>(a, st);                                             \
-      case 7: return launch_fused_ns<7, CLASSIC_, TMA_>(a, st);                                             \
-      case 8: return launch_fused_ns<8, CLASSIC_, TMA_>(a, st);                                             \
-      case 9: return launch_fused_ns<9, CLASSIC_, TMA_>(a, st);                                             \
-      case 10: return launch_fused_ns<10, CLASSIC_, TMA_>(a, st);                                           \
-      case 11: return launch_fused_ns<11, CLASSIC_, TMA_>(a, st);                                           \
-      case 12: return launch_fused_ns<12, CLASSIC_, TMA_>(a, st);                                           \
-      case 13: return launch_fused_ns<13, CLASSIC_, TMA_>(a, st);                                           \
-      case 14: return launch_fused_ns<14, CLASSIC_, TMA_>(a, st);                                           \
-      case 15: return launch_fused_ns<15, CLASSIC_, TMA_>(a, st);                                           \
-      case 16: return launch_fused_ns<16, CLASSIC_, TMA_>(a, st);                                           \
-      default: return cudaErrorInvalidValue;                                                                \
-    }                                                                                                       \
+#define CTCB200_FUSED_CASE(n) \
+  case n:                     \
+    return launch_fused_ns<n, CLASSIC_, TMA_, BF16_>(a, st);
+#define CTCB200_DEFINE_FUSED_VARIANT(CLASSIC__, TMA__, BF16__)                                                       \
+  template <>                                                                                                       \
+  cudaError_t launch_fused_variant<CLASSIC__, TMA__, BF16__>(const FusedArgs& a, cudaStream_t st) {                 \
+    constexpr bool CLASSIC_ = CLASSIC__, TMA_ = TMA__, BF16_ = BF16__;                                               \
+    switch (a.p.NS) {                                                                                               \
+      CTCB200_FUSED_CASE(1) CTCB200_FUSED_CASE(2) CTCB200_FUSED_CASE(3) CTCB200_FUSED_CASE(4)                       \
+      CTCB200_FUSED_CASE(5) CTCB200_FUSED_CASE(6) CTCB200_FUSED_CASE(7) CTCB200_FUSED_CASE(8)                       \
+      CTCB200_FUSED_CASE(9) CTCB200_FUSED_CASE(10) CTCB200_FUSED_CASE(11) CTCB200_FUSED_CASE(12)                    \
+      CTCB200_FUSED_CASE(13) CTCB200_FUSED_CASE(14) CTCB200_FUSED_CASE(15) CTCB200_FUSED_CASE(16)                   \
+      default: return cudaErrorInvalidValue;                                                                        \
+    }                                                                                                               \
   }
 
 }  // namespace ctcb200

@@ -1,6 +1,6 @@
-// Instantiations of the fused kernel: simplified variant, rows moved by 4-byte cp.async (unaligned rows).
+// Instantiations of the fused kernel: simplified variant, 4-byte cp.async row mover (one translation unit per combination so that they compile in parallel).
 #include "kf_fused.cuh"
 
 namespace ctcb200 {
-CTCB200_DEFINE_FUSED_VARIANT(false, false)
-}  // namespace ctcb200
+CTCB200_DEFINE_FUSED_VARIANT(false, false, false)
+}

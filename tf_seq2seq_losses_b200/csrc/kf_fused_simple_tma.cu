@@ -1,6 +1,6 @@
-// Instantiations of the fused kernel: simplified variant, rows moved by 1-D TMA.
+// Instantiations of the fused kernel: simplified variant, TMA row mover (one translation unit per combination so that they compile in parallel).
 #include "kf_fused.cuh"
 
 namespace ctcb200 {
-CTCB200_DEFINE_FUSED_VARIANT(false, true)
-}  // namespace ctcb200
+CTCB200_DEFINE_FUSED_VARIANT(false, true, false)
+}
