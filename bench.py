@@ -384,6 +384,7 @@ def main():
     if not args.no_e2e:
         del grad, ws
         torch.cuda.empty_cache()
+        affinity_before = os.sched_getaffinity(0)
         bind_to_gpu_numa_node(local_rank)
         n_slices = max(1, min(8, local_B // 16))     # >= 16 utterances per slice: below that the T-step chain, not the copy, paces a slice
         ctx = _lib.HostContext(local_B, T, V, L, 0, vid, L + 1, device=local_rank, num_slices=n_slices,

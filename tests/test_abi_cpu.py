@@ -87,7 +87,15 @@ def test_workspace_classes_and_kernel_choice():
     assert names(_lib.Desc(32, 500, 29, 100, 0, _lib.CLASSIC, 101, _lib.FORCE_FUSED)) == "kf_fused"
     time_major = _lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, _lib.TIME_MAJOR)
     assert ws(time_major, _lib.WS_LOSS_GRAD_LOGITS) == ws(north_star, _lib.WS_LOSS_GRAD_LOGITS)      # scratch keeps its layout
-    assert ws(_lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, 16), _lib.WS_LOSS_GRAD) == 0     # unknown flag bit
+    assert ws(_lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, 64), _lib.WS_LOSS_GRAD) == 0     # unknown flag bit
+    assert ws(_lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, _lib.GRAD_BF16), _lib.WS_LOSS_GRAD) == 0   # needs LOGITS_BF16
+    bf16 = _lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, _lib.LOGITS_BF16 | _lib.GRAD_BF16)
+    assert ws(bf16, _lib.WS_LOSS_GRAD_LOGITS) == ws(north_star, _lib.WS_LOSS_GRAD_LOGITS) and names(bf16) == "kf_fused"
+    # bf16 rows exist in the fused kernel only: a narrow vocabulary in a small batch takes it as well
+    assert names(_lib.Desc(32, 500, 32, 100, 0, _lib.CLASSIC, 101, _lib.LOGITS_BF16)) == "kf_fused"
+    # the small-batch (split) plan does not change the workspace class sizes' ordering
+    slice32 = _lib.Desc(32, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, 0)
+    assert names(slice32) == "kf_fused" and ws(slice32, _lib.WS_LOSS_GRAD_LOGITS) * 2 < ws(slice32, _lib.WS_LOSS_GRAD)
     full_sweep = _lib.Desc(2048, 1600, 5000, 400, 0, _lib.CLASSIC, 401, 0)   # BASELINE configs[4] on one GPU
     assert names(full_sweep) == "kf_fused"
     assert ws(full_sweep, _lib.WS_LOSS_GRAD_LOGITS) + 2 * 2048 * 1600 * 5000 * 4 < 180e9      # fits one B200

@@ -299,7 +299,10 @@ def test_logarithmic_logproba_gradient_is_native_log_domain(variant):
     assert np.array_equal(np.isneginf(got), np.isneginf(want))
     fin = np.isfinite(want)
     assert (want[fin] < -110.0).any(), "the case must reach below float32's exp underflow"
-    assert np.max(np.abs(got[fin] - want[fin]) / np.maximum(1.0, np.abs(want[fin]))) <= 2e-5
+    # float32 log-domain arithmetic on terms as large as the loss (~900 here, one ulp = 6e-5): a few ulps of those, plus
+    # the usual relative bar on the value itself
+    tol = 5e-7 * float(np.max(ref.loss[np.isfinite(ref.loss)])) + 2e-5 * np.maximum(1.0, np.abs(want[fin]))
+    assert np.all(np.abs(got[fin] - want[fin]) <= tol), float(np.max(np.abs(got[fin] - want[fin])))
     # and exp(.) of it is the gradient the other entry point returns
     assert np.max(np.abs(np.exp(got) + data.gradient.cpu().numpy())) <= GRAD_ATOL_SHORT
 

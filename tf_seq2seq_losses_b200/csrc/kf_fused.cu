@@ -37,7 +37,7 @@ static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, 
   const int mode = ow > 0 ? g_plan_override[4] : 0, want_half = (mode & 2) ? 0 : 1;
   if (ow > 0) {
     const int sl = g_plan_override[1], xa = g_plan_override[2], r = g_plan_override[3], sp = mode & 1;
-    if (ow <= (sp ? kMaxWorkersSplit : kMaxWorkers) && sl >= 2 && sl <= 3 && xa >= 0 && xa <= 1 && r >= 1 && r <= 2 * ow &&
+    if (ow <= (sp ? (p.NS > 8 ? 6 : kMaxWorkersSplit) : kMaxWorkers) && sl >= 2 && sl <= 3 && xa >= 0 && xa <= 1 && r >= 1 && r <= 2 * ow &&
         (!sp || tma_ok) && fits(p, ow, sl, xa, r, sp ? 1 : 2, kSmemPerSm, want_half, half)) {
       *W = ow; *SL = sl; *XA = xa; *R = r; *split = sp;
       return true;
@@ -46,11 +46,15 @@ static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, 
   if (tma_ok && 2 * p.B <= kNumSms) {
     static const int scand[8][4] = {{8, 3, 1, 16}, {8, 2, 1, 16}, {8, 2, 0, 16}, {6, 3, 1, 12}, {6, 2, 1, 12}, {6, 2, 0, 12},
                                     {4, 3, 1, 8}, {4, 2, 0, 8}};
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < 8; ++c) {
+      // Registers are a per-scheduler resource (16 K each): nine warps put three on one scheduler, which holds at most
+      // 112 registers per thread.  The wide-state kernels (NS > 8, up to 224 registers) run seven warps, two per scheduler.
+      if (p.NS > 8 && scand[c][0] > 6) continue;
       if (fits(p, scand[c][0], scand[c][1], scand[c][2], scand[c][3], 1, kSmemPerSm, want_half, half)) {
         *W = scand[c][0]; *SL = scand[c][1]; *XA = scand[c][2]; *R = scand[c][3]; *split = 1;
         return true;
       }
+    }
   }
   // {workers per side, row buffers per worker, extra phase-A row buffer, ring depth}.  Measured on B200 (B=256 T=1000
   // V=1024): 4 workers beat 3 for both variants; the classic variant (two state planes) only fits 4 workers next to a

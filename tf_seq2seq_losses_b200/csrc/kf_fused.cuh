@@ -44,10 +44,10 @@ constexpr int kMaxWorkersSplit = 8;  // ... when each side has a CTA (and an SM,
 
 // A/B switches (developer builds, tools/build_variant.sh): the recursion warp's frame order, the wait watchdog
 #ifndef CTCB200_REC_REORDER
-#define CTCB200_REC_REORDER 1
+#define CTCB200_REC_REORDER 0      // 1: await the next frame's inputs before stepping (measured slower: 622 vs 608 us, classic 1011 vs 926)
 #endif
 #ifndef CTCB200_WATCHDOG
-#define CTCB200_WATCHDOG 1
+#define CTCB200_WATCHDOG 0      // 1: every mbarrier wait counts its polls and traps instead of hanging (costs ~15 % at B=256)
 #endif
 
 // ---- PTX helpers -----------------------------------------------------------------------------------------------
@@ -271,11 +271,22 @@ __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {      // ro
   } while (0)
 #endif
 
+#ifdef CTCB200_WATCHDOG_VERBOSE
+#define CTCB200_TRACE(fmt, ...)                                                                         \
+  do {                                                                                                  \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) printf("trace warp %d: " fmt "\n", (int)(threadIdx.x >> 5), __VA_ARGS__); \
+  } while (0)
+#else
+#define CTCB200_TRACE(fmt, ...) \
+  do {                          \
+  } while (0)
+#endif
+
 // ---- shared-memory layout (one definition for host sizing and device carving) ---------------------------------------
 struct FusedLayout {
   int W, R, SL, XA;         // workers per side, ring depth (W..2W), row buffers per worker, extra phase-A row buffers (0/1)
   int half;                 // 1: phase A stores every second state row only, phase B derives the others (see HALF below)
-  int off_xch, off_xoff, off_side0, total, xch_aliased;
+  int off_xch, off_xoff, off_flag, off_side0, total, xch_aliased;
   // offsets inside a side block
   int s_ctl, s_bar, s_row, s_aux, s_ringd, s_ringh, side_bytes;
   // offsets inside the aux block (phase B view)
@@ -295,7 +306,15 @@ __host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a *
 // it with the inputs of its own frame -- it holds them anyway -- and hands the result to the worker of the frame before
 // through shared memory (`fwd`, one vector per even ring slot, barrier fwd_full).  Halves the state traffic (0.40 ->
 // 0.20 GB at B=256 T=1000 U=201) and the global stores of the recursion warps.
-__host__ __device__ inline bool fused_half_ok(int S, int W, int R) { return S == 1 && (W & 1) == 0 && (R & 1) == 0; }
+// Compiled out by default: measured on B200 (simplified, T=1000 V=1024 L=200) it is SLOWER than storing every row -- B=256
+// 609 vs 592 us, B=128 507 vs 474 us: the even frames now wait for the worker of the next frame, and at 95 % of the
+// copy bandwidth the 5 % of traffic it saves does not buy that back.  -DCTCB200_HALF_SCRATCH=1 brings it back.
+#ifndef CTCB200_HALF_SCRATCH
+#define CTCB200_HALF_SCRATCH 0
+#endif
+__host__ __device__ inline bool fused_half_ok(int S, int W, int R) {
+  return CTCB200_HALF_SCRATCH && S == 1 && (W & 1) == 0 && (R & 1) == 0;
+}
 __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL, int XA, int R, int sides = 2,
                                                     int half = 0) {
   FusedLayout f;
@@ -309,6 +328,7 @@ __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int 
   f.xch_aliased = (R >= S) ? 1 : 0;       // a side's exchange vector (S*Upad floats) fits its input ring (R*Upad floats)
   f.off_xch = o;  o += f.xch_aliased ? 0 : sides * S * Upad * 4;
   f.off_xoff = o; o += 2 * 8;
+  f.off_flag = o; o += 8;                 // CTA-wide facts gathered in the prologue (see fused_body)
   o = fl_align(o, 128);
   int s = 0;
   // Two sets of every barrier, one per phase: all of them are initialised once at kernel start and none is ever
@@ -415,9 +435,9 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
   float* g_state = a.stateT + ((size_t)b * a.p.T + t_first) * (size_t)(S_ * kUpad);
   double* g_off = a.coff + (size_t)b * a.p.T + t_first;
   const ptrdiff_t g_step = (ptrdiff_t)t_step * (S_ * kUpad);
-  // Order inside a frame: the loads of the frame's inputs are issued first (their barrier was passed in the previous
-  // iteration), the publication of the pre-step state hides their latency, then the NEXT frame's barrier is awaited --
-  // its round trip is off the chain of the step that follows, whose result nobody needs before those inputs exist.
+  // CTCB200_REC_REORDER=1 (off: measured slower) changes the order inside a frame: the loads of the frame's inputs are
+  // issued first (their barrier was passed in the previous iteration), the publication of the pre-step state hides their
+  // latency, then the NEXT frame's barrier is awaited before the step.
 #if CTCB200_REC_REORDER
   if (count > 0) TIMED(3, mbar_wait(sv.full_d, 0u, 1));         // the first frame's inputs are in the ring
 #endif
@@ -435,10 +455,12 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
     if (CLASSIC && SIDE == 0) alpha_classic_prepare<NS>(v0, v1, lb, S, x);
     const float* out0 = !CLASSIC ? v0 : (SIDE == 0 ? x : v1);
     if (!phase_b) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sv.empty + slot);             // the inputs are in registers: the slot may be refilled
       // -> global scratch for the other side's phase B, which walks these frames in reverse order (frame i here is its
       // frame count-1-i): with HALF only its odd frames are stored.  A loss-only call stops at the middle: nobody will
       // read the scratch.
-      if (a.grad != nullptr && (!f.half || ((count - 1 - i) & 1))) {
+      if (a.grad != nullptr && (!(CTCB200_HALF_SCRATCH && f.half) || ((count - 1 - i) & 1))) {
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
           stg_keep(g_state + j * kWarp + lane, out0[j]);
@@ -448,8 +470,6 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
       }
       g_state += g_step;
       g_off += t_step;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sv.empty + slot);             // the inputs are in registers: the slot may be refilled
     } else {
       if (i >= R) TIMED(6, mbar_wait(sv.empty + slot, use_par ^ 1u, 2));   // previous frame of the slot is finished
       float* dst = sv.rings + slot * (S_ * kUpad);
@@ -461,6 +481,7 @@ __device__ __forceinline__ void rec_phase(const FusedArgs& a, const FusedLayout&
       if (lane == 0) sv.ringc[slot] = c;
       __syncwarp();
       if (lane == 0) mbar_arrive(sv.full_s + slot);
+      CTCB200_TRACE("rec side %d frame %d: state published (slot %d)", SIDE, i, slot);
     }
     const int nslot = (slot + 1 == R) ? 0 : slot + 1;
     const unsigned npar = (nslot == 0) ? (use_par ^ 1u) : use_par;
@@ -558,7 +579,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   // HALF (see fused_layout): only the rows of odd frames (counted from the middle) were stored.  W is even, so a worker
   // sees frames of one parity: odd workers read stored rows -- fetched a whole iteration ahead -- and derive the state of
   // the frame before; even workers receive that through `fwd` and never touch the global scratch.
-  const bool half = PHASE_B && !CLASSIC && f.half;
+  const bool half = CTCB200_HALF_SCRATCH && PHASE_B && !CLASSIC && f.half;
   const bool odd_w = half && (w & 1), even_w = half && !(w & 1);
   // the other side's stored state of frame `tt`: async copy into this worker's staging buffer
   auto fetch_state = [&](int tt) {
@@ -597,6 +618,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
         else cst_next = (i + W + 1 < count) ? coff_b[tn + t_step] : 0.0;
       }
     }
+    CTCB200_TRACE("worker %d phase %d frame %d of %d: start (slot %d par %u)", w, (int)PHASE_B, i, count, slot, use_par);
     // ---- prefetch (phase A): the buffer row n-1 used is free as soon as this iteration starts ----
     if (!PHASE_B && n + SL - 1 < n_my) load_row((rs == 0) ? SL - 1 : rs - 1, t + (SL - 1) * W * t_step);
     TIMED(2, mbar_wait(bars + rs, (par >> rs) & 1u, 3));          // the row has landed
@@ -686,6 +708,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     if (lane == 0) sv.ringh[slot] = h;
     __syncwarp();
     if (lane == 0) mbar_arrive(sv.full_d + slot);
+    CTCB200_TRACE("worker %d phase %d frame %d: inputs published", w, (int)PHASE_B, i);
 #ifdef CTCB200_FUSED_TIMING
     tm[3] += clock64() - t_g0;   // workers: ring wait + gather + publish
 #endif
@@ -708,6 +731,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       for (int j = 0; j < NS; ++j) fw[j * kWarp + lane] = st[j];
       __syncwarp();
       if (lane == 0) mbar_arrive(sv.fwd_full + sp);
+      CTCB200_TRACE("worker %d frame %d: derived state forwarded to slot %d", w, i, sp);
     }
 
     // ---- stage 1b (phase B): the dense softmax part of the gradient row, in place, while the recursion catches up.
@@ -789,7 +813,9 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 
     // ---- stage 2 (phase B): occupancies of the frame, scattered into the row; then the row leaves by TMA ----
     if (PHASE_B) {
+      CTCB200_TRACE("worker %d frame %d: softmax + prefetch done, waiting for the state", w, i);
       TIMED(5, mbar_wait(sv.full_s + slot, use_par, 5));          // the running side's state for this frame is published
+      CTCB200_TRACE("worker %d frame %d: state there", w, i);
       const float* other = stb;                                  // the other side's state for this frame
       if (!even_w) {
         TIMED(7, fused_cp_async_wait_all());
@@ -816,6 +842,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 #ifdef CTCB200_FUSED_TIMING
       const long long t_o0 = clock64();
 #endif
+      CTCB200_TRACE("worker %d frame %d: other state ready", w, i);
       const float* ring_state = sv.rings + slot * (S * kUpad);
       const float K = (float)(lossd_mid + sv.ringc[slot] + cst);   // loss + both renormalisation offsets
       const float* A = (side == 0) ? ring_state : other;       // alpha[t]
@@ -879,9 +906,17 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
       // The blank's occupancy is the complement of the others: every alignment emits exactly one symbol per frame, so
       // sum_k occ[t,k] = 1 (simplified_ctc_loss.py:498-501 / classic_ctc_loss.py:608-614 compute the same number as
       // exp(loss + h + logsumexp_l(alpha + beta)); the complement needs one warp sum instead of a second log-sum-exp).
+      CTCB200_TRACE("worker %d frame %d: occupancies computed", w, i);
       float osum = 0.0f;
 #pragma unroll
       for (int j = 0; j < NS; ++j) osum += occ[j];
+#ifdef CTCB200_WATCHDOG_VERBOSE
+      {
+        const unsigned f0 = __shfl_sync(kFull, ll.flags, 0), any = __ballot_sync(kFull, ll.flags & 8u);
+        if (blockIdx.x == 0 && lane == 0 && i < 2) printf("trace warp %d: flags lane0 %x ballot(bit3) %08x ok_nb %x\n", (int)(threadIdx.x >> 5), f0, any, ll.ok_nb);
+      }
+#endif
+#ifndef CTCB200_DBG_NO_BLANKBLOCK
       if (ll.any_blank_label()) {
         // Undefined input (a real label equal to the blank): the reference overrides the blank column with the horizontal
         // term alone, so the emission occupancy of such states vanishes from the row and from its total -- the softmax
@@ -900,21 +935,30 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           __syncwarp();
         }
       }
+#endif
+      CTCB200_TRACE("worker %d frame %d: before scatter", w, i);
       // Scatter: row[token] -= d_loss * occ.  Shared-memory float atomics were measured against shuffle-combined,
       // conflict-mask-guarded and statically ranked conflict-free read-modify-write passes (round 1) and against a static
       // leader / follower plan that needs no atomics at all (round 2: 671 vs 573 us at B=256, 347 vs 323 us at B=32); the
       // atomics won every time at V = 1024 and tied at V = 5000.
 #pragma unroll
       for (int j = 0; j < NS; ++j)
+#ifdef CTCB200_DBG_PLAIN_SCATTER
+        if (ll.nb(j) && occ[j] > 0.0f) row[tok[j]] -= dl * occ[j];
+#else
         if (ll.nb(j) && occ[j] > 0.0f) atomicAdd(&row[tok[j]], -dl * occ[j]);
+#endif
+      CTCB200_TRACE("worker %d frame %d: atomics issued", w, i);
       __syncwarp();
 #ifdef CTCB200_FUSED_TIMING
       const long long t_o2 = clock64();
       tm[10] += t_o2 - t_o1;
 #endif
+      CTCB200_TRACE("worker %d frame %d: scattered", w, i);
       const float occ_blank = 1.0f - warp_sum(osum);
       if (lane == 0) row[p.blank] -= dl * occ_blank;
       __syncwarp();
+      CTCB200_TRACE("worker %d frame %d: blank done", w, i);
       float* gdst = a.grad + row_offset(p, b, t);
       if (BF16 && p.grad_bf16) {
         // narrow the finished row in place (element k -> bytes 2k..2k+1: again only already-read bytes are overwritten)
@@ -940,6 +984,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
         __syncwarp();
       }
       if (lane == 0) mbar_arrive(sv.empty + slot);              // ring slot and stb are free again
+      CTCB200_TRACE("worker %d frame %d: row done", w, i);
 #ifdef CTCB200_FUSED_TIMING
       tm[11] += clock64() - t_o2;
 #endif
@@ -1015,10 +1060,19 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
     if (emits(lane * NS - 1, tl)) ll.flags |= (tl != p.blank) ? 3u : 1u;
   }
   {
+    // "Some label of this utterance equals the blank" is gathered through a shared-memory word and plain barriers.  (NOT
+    // __syncthreads_or: its result is only consumed deep inside the workers' phase-B loop, and nvcc 12.9 sank the
+    // BAR.RED.OR itself down to that use -- a CTA-wide barrier executed per row by the worker warps alone, which
+    // deadlocked long utterances and let the recursion warps of short ones run ahead of their inputs.)
+    volatile int* cta_flag = reinterpret_cast<volatile int*>(smem + f.off_flag);
+    if (tid == 0) *cta_flag = 0;
+    __syncthreads();
     bool blank_label = false;
 #pragma unroll
     for (int j = 0; j < NS; ++j) blank_label |= ll.ok(j) && !ll.nb(j);
-    if (__syncthreads_or(blank_label)) ll.flags |= 8u;
+    if (blank_label) *cta_flag = 1;
+    __syncthreads();
+    if (*cta_flag != 0) ll.flags |= 8u;
   }
 
   long long tm[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1026,34 +1080,16 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
 #ifdef CTCB200_FUSED_TIMING
   const long long t_start = clock64();
 #endif
-  // recursion state (only meaningful in the two recursion warps)
-  float v0[NS], v1[NS];
-  double c = 0.0;
-  LabelBits<NS> lb;
-  if (CLASSIC) lb = make_label_bits<NS>(p, b, L, lane);
-#pragma unroll
-  for (int j = 0; j < NS; ++j) {
-    const int l = lane * NS + j;
-    if (side == 0) {            // alpha[0] = log one_hot(state 0, closed)
-      v0[j] = (l == 0) ? 0.0f : kNegInf;
-      v1[j] = kNegInf;
-    } else {                    // beta[n_t] = log one_hot(label_length), both states
-      v0[j] = (l == L) ? 0.0f : kNegInf;
-      v1[j] = v0[j];
-    }
-  }
-
   // ------------------------------------------------ phase A, the middle, phase B -----------------------------------------
-  // One rolled loop over the two phases: each recursion routine is inlined once per side instead of once per (side,
-  // phase), which halves the instruction footprint of the recursion warps.
+  // The role branch sits OUTSIDE the phase loop: the recursion warps never carry the workers' label registers and the
+  // workers never carry the recursion state (with one loop body serving both roles every one of them stayed live through
+  // the other role's code, and the recursion loops of the classic variant reloaded eight spilled registers per frame).
   bool dead = false;                 // no feasible alignment: loss = +inf, zero gradient
   double lossd_mid = 0.0;            // -log Z, known after phase A
 #ifdef CTCB200_FUSED_TIMING
   long long t_mid = 0;
 #endif
-#pragma unroll 1
-  for (int ph = 0; ph < 2; ++ph) {
-    int cnt, tf;
+  auto phase_frames = [&](int ph, int& cnt, int& tf) {
     if (ph == 0) {
       cnt = (side == 0) ? M : n_t - M;
       tf = (side == 0) ? 0 : n_t - 1;
@@ -1061,33 +1097,15 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
       cnt = (side == 0) ? n_t - M : M;
       tf = (side == 0) ? M : M - 1;
     }
-    const int ts = (side == 0) ? 1 : -1;
-    const SideView sv = side_view(smem, f, my, ph);      // this phase's barrier set
-    if (role == 0) {
-      if (side == 0) rec_phase<NS, CLASSIC, 0>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
-      else rec_phase<NS, CLASSIC, 1>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
-    } else if (ph == 0) {
-      worker_phase<NS, CLASSIC, false, TMA, BF16>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, ll, lane, tm);
-    } else {
-      worker_phase<NS, CLASSIC, true, TMA, BF16>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, ll, lane, tm);
-    }
-    if (ph == 1) break;
+  };
+  const int ts = (side == 0) ? 1 : -1;
+  // The middle, executed by every thread: log Z from the two exchange vectors, then the barrier that lets phase B reuse
+  // the shared memory.  Returns false when the call ends here (loss-only call, or an infeasible sample).
+  auto middle = [&]() {
 #ifdef CTCB200_FUSED_TIMING
     tm[0] = clock64() - t_start;
     t_mid = clock64();
 #endif
-    // ---------------------------------------------- the middle ---------------------------------------------------------
-    // Each recursion warp leaves its state vector in ITS OWN side's exchange slot.  When shared memory is short the slot
-    // aliases that side's input ring, which is idle by now: the warp has consumed every frame its workers produced.
-    if (role == 0) {
-      float* dst = xch_of(my);
-#pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        dst[j * kWarp + lane] = v0[j];
-        if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
-      }
-      if (lane == 0) xoff[my] = c;
-    }
     LseAcc zacc;
     double off_sum;
     if (!SPLIT) {
@@ -1115,28 +1133,92 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
       // Loss-only call (the forward pass of a training step, or evaluation): -log Z is known at the middle, so the call
       // costs phase A alone -- half the chain, one read of the logits, nothing written but the loss.
       if (side == 0 && tid == 0) a.loss[b] = dead ? INFINITY : (float)lossd_mid;
-      return;
+      return false;
     }
-    if (dead) break;
-  }
-
+    return !dead;
+  };
 #ifdef CTCB200_FUSED_TIMING
-  tm[1] = clock64() - t_mid;
-  if (a.dbg != nullptr && lane == 0)
-    for (int q = 0; q < 12; ++q) a.dbg[((size_t)b * (2 * (W + 1)) + side * (W + 1) + role) * 12 + q] = tm[q];
+  auto dump_timing = [&]() {
+    tm[1] = clock64() - t_mid;
+    if (a.dbg != nullptr && lane == 0)
+      for (int q = 0; q < 12; ++q) a.dbg[((size_t)b * (2 * (W + 1)) + side * (W + 1) + role) * 12 + q] = tm[q];
+  };
 #endif
-  // ------------------------------------------------ loss and the rows nobody owns --------------------------------------
-  if (side == 0 && role == 0) {
-    // loss = -alpha[T, label_length] (classic_ctc_loss.py:152-165 / simplified_ctc_loss.py:73-83); frames beyond n_t
-    // leave it unchanged.
+
+  if (role == 0) {
+    // ---- a recursion warp: state in registers ----
+    float v0[NS], v1[NS];
+    double c = 0.0;
+    LabelBits<NS> lb;
+    if (CLASSIC) lb = make_label_bits<NS>(p, b, L, lane);
 #pragma unroll
-    for (int j = 0; j < NS; ++j)
-      if (lane * NS + j == L) {
-        const double ld = dead ? (double)INFINITY : -((double)(CLASSIC ? lse2(v0[j], v1[j]) : v0[j]) + c);
-        a.loss[b] = (float)ld;
+    for (int j = 0; j < NS; ++j) {
+      const int l = lane * NS + j;
+      if (side == 0) {            // alpha[0] = log one_hot(state 0, closed)
+        v0[j] = (l == 0) ? 0.0f : kNegInf;
+        v1[j] = kNegInf;
+      } else {                    // beta[n_t] = log one_hot(label_length), both states
+        v0[j] = (l == L) ? 0.0f : kNegInf;
+        v1[j] = v0[j];
       }
-  }
-  if (role > 0) {     // frames beyond logit_length, or every frame of an infeasible sample: exact zeros
+    }
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {
+      int cnt, tf;
+      phase_frames(ph, cnt, tf);
+      const SideView sv = side_view(smem, f, my, ph);      // this phase's barrier set
+      if (side == 0) rec_phase<NS, CLASSIC, 0>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
+      else rec_phase<NS, CLASSIC, 1>(a, f, sv, b, cnt, tf, ts, ph == 1, v0, v1, c, lb, lane, tm);
+      if (ph == 1) break;
+      // The warp leaves its state vector in ITS OWN side's exchange slot.  When shared memory is short the slot aliases
+      // that side's input ring, which is idle by now: the warp has consumed every frame its workers produced.
+      float* dst = xch_of(my);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        dst[j * kWarp + lane] = v0[j];
+        if (CLASSIC) dst[kUpad + j * kWarp + lane] = v1[j];
+      }
+      if (lane == 0) xoff[my] = c;
+      if (!middle()) {
+        if (a.grad == nullptr) return;
+        break;
+      }
+    }
+#ifdef CTCB200_FUSED_TIMING
+    dump_timing();
+#endif
+    if (side == 0) {
+      // loss = -alpha[T, label_length] (classic_ctc_loss.py:152-165 / simplified_ctc_loss.py:73-83); frames beyond n_t
+      // leave it unchanged.
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+        if (lane * NS + j == L) {
+          const double ld = dead ? (double)INFINITY : -((double)(CLASSIC ? lse2(v0[j], v1[j]) : v0[j]) + c);
+          a.loss[b] = (float)ld;
+        }
+    }
+  } else {
+    // ---- a row worker ----
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {
+      int cnt, tf;
+      phase_frames(ph, cnt, tf);
+      const SideView sv = side_view(smem, f, my, ph);
+      if (ph == 0) {
+        worker_phase<NS, CLASSIC, false, TMA, BF16>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, ll, lane, tm);
+      } else {
+        worker_phase<NS, CLASSIC, true, TMA, BF16>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, ll, lane, tm);
+        break;
+      }
+      if (!middle()) {
+        if (a.grad == nullptr) return;
+        break;
+      }
+    }
+#ifdef CTCB200_FUSED_TIMING
+    dump_timing();
+#endif
+    // frames beyond logit_length, or every frame of an infeasible sample: exact zeros
     const int widx = side * W + (role - 1);
     for (int r = (dead ? 0 : n_t) + widx; r < p.T; r += 2 * W) {
       if (BF16 && p.grad_bf16)       // a bf16 row is V/2 floats wide (V % 8 == 0)

@@ -13,13 +13,15 @@ T, V, L = (int(x) for x in os.environ.get("CTCB200_TVL", "1000,1024,200").split(
 variant = _lib.CLASSIC if (len(sys.argv) > 1 and sys.argv[1] == "classic") else _lib.SIMPLIFIED
 Bs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [256, 128, 64, 32, 16]
 lib = _lib.load()
+if os.environ.get("CTCB200_PLAN"):       # "W,SL,XA,R,mode" -> ctcb200_debug_fused_plan
+    lib.ctcb200_debug_fused_plan(*(int(x) for x in os.environ["CTCB200_PLAN"].split(",")))
 g = torch.Generator().manual_seed(0)
 for B in Bs:
     logits = torch.randn((B, T, V), generator=g).cuda()
     labels = torch.randint(1, V, (B, L), generator=g, dtype=torch.int32).cuda()
     ll = torch.full((B,), L, dtype=torch.int32).cuda()
     tl = torch.full((B,), T, dtype=torch.int32).cuda()
-    desc = _lib.make_desc(logits, labels, 0, variant, L + 1, 0)
+    desc = _lib.make_desc(logits, labels, 0, variant, L + 1, int(os.environ.get("CTCB200_FLAGS", "0")))
     n = lib.ctcb200_workspace_bytes(ctypes.byref(desc), _lib.WS_LOSS_GRAD)
     ws = torch.empty(n, dtype=torch.uint8, device="cuda")
     loss = torch.empty(B, device="cuda")
@@ -41,6 +43,6 @@ for B in Bs:
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / 20)
     alg = B * (8 * T * V + 4 * L + 12)
-    print(f"B={B:4d} T={T} V={V} L={L} {'classic' if variant == _lib.CLASSIC else 'simplified':10s} {best*1e3:8.1f} us  "
+    print(f"B={B:4d} T={T} V={V} L={L} {'classic' if variant == _lib.CLASSIC else 'simplified':10s} {lib.ctcb200_stage_names(ctypes.byref(desc)).decode()[:9]:9s} {best*1e3:8.1f} us  "
           f"{B/best*1e3:10.0f} samples/s  {alg/best/1e6/6553*100:5.1f}% of 6553 GB/s   {best*1e6/T:6.1f} ns/frame", flush=True)
     del logits, grad, ws
