@@ -307,11 +307,16 @@ def test_logarithmic_logproba_gradient_is_native_log_domain(variant):
     assert np.max(np.abs(np.exp(got) + data.gradient.cpu().numpy())) <= GRAD_ATOL_SHORT
 
 
+@pytest.mark.parametrize("schedule", ["eager", "deferred"])
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
-def test_cuda_graph_capture_and_replay(variant):
+def test_cuda_graph_capture_and_replay(variant, schedule, monkeypatch):
     """The reference runs under tf.function / autograph (tests/test_simplified_ctc_loss.py:293-320,
     tests/test_hessian.py:213-257).  The equivalent here: loss + backward captured in a torch.cuda.CUDAGraph (no host
-    synchronisation, no allocation outside the graph's pool) and replayed on new data, bit-identical to the eager call."""
+    synchronisation, no allocation outside the graph's pool) and replayed on new data, bit-identical to the un-captured
+    call -- for both schedules of the training step (gradient computed in the forward pass and scaled in backward, or
+    loss-only forward and the gradient computed in backward with d_loss inside the kernel; base_loss.py)."""
+    from tf_seq2seq_losses_b200 import base_loss
+    monkeypatch.setattr(base_loss, "EAGER_MAX_ELEMENTS", (1 << 24) if schedule == "eager" else 0)
     B, T, V, L = 6, 50, 128, 10
     fn = _fn(variant)
     logits0, labels, ll, tl = random_inputs(B, T, V, L, seed=41)

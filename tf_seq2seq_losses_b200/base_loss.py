@@ -211,35 +211,55 @@ def ctc_loss_from_logproba(labels, logprobas, label_length, logit_length, blank_
 
 
 # ---- fused logits path (the hot path): log-softmax + loss + d/dlogits in one library call ---------------------
-class _FusedLossFn(torch.autograd.Function):
-    """ctc_loss (base_loss.py:38-68) with the log-softmax (tools.py:27-40) and its backward fused into the kernels.
+# Two schedules for a training step (forward, then backward with an upstream gradient d_loss):
+#   deferred  forward = loss-only call (the fused kernel stops at the middle: half the T-step chain, logits read once);
+#             backward = the full loss+gradient call with d_loss applied inside the kernel.  No [B,T,V] tensor lives
+#             between the passes, none is re-scaled.  Best where the call is bandwidth-bound: B=256 T=1000 V=1024
+#             0.25 + 0.58 ms against 0.58 + 0.35 ms (the extra pass of the eager multiply).
+#   eager     forward = the full call (d_loss = 1), the gradient is kept; backward = d_loss[:,None,None] * gradient like
+#             the reference (base_loss.py:150-153).  Best where the T-step chain is the runtime and a [B,T,V] pass is
+#             cheap: the reference's benchmark shape B=256 T=255 V=32 takes 170 us this way, 240 us deferred.
+# Below EAGER_MAX_ELEMENTS logits elements the eager schedule is used.
+EAGER_MAX_ELEMENTS = 1 << 24
 
-    Like the reference's forward_fn (base_loss.py:140-155) the forward pass computes the loss alone -- a loss-only call of
-    the fused kernel, half the work -- and the gradient is produced in the backward pass, where the upstream gradient
-    d_loss is known and is applied inside the kernel (no [B,T,V] tensor is kept between the passes, none is re-scaled)."""
+
+class _FusedLossFn(torch.autograd.Function):
+    """ctc_loss (base_loss.py:38-68) with the log-softmax (tools.py:27-40) and its backward fused into the kernels;
+    forward_fn / gradient_fn of the reference (base_loss.py:140-175) in one of the two schedules above."""
 
     @staticmethod
     def forward(ctx, logits, labels, label_length, logit_length, desc):
-        loss = _lib.loss_only(desc, logits.detach().contiguous(), labels, label_length, logit_length)
+        x = logits.detach().contiguous()
         ctx.desc, ctx.aux = desc, (labels, label_length, logit_length)
-        ctx.save_for_backward(logits)
+        ctx.eager = bool(logits.requires_grad and x.numel() < EAGER_MAX_ELEMENTS)
+        if ctx.eager:
+            loss, grad, _ = _lib.loss_grad(desc, x, labels, label_length, logit_length)
+            ctx.save_for_backward(logits, grad)
+        else:
+            loss = _lib.loss_only(desc, x, labels, label_length, logit_length)
+            ctx.save_for_backward(logits)
         return loss
 
     @staticmethod
     def backward(ctx, d_loss):
-        (logits,) = ctx.saved_tensors
-        return _FusedGradFn.apply(logits, d_loss, ctx.desc, ctx.aux), None, None, None, None
+        logits = ctx.saved_tensors[0]
+        unit_grad = ctx.saved_tensors[1] if ctx.eager else None
+        return _FusedGradFn.apply(logits, d_loss, unit_grad, ctx.desc, ctx.aux), None, None, None, None
 
 
 class _FusedGradFn(torch.autograd.Function):
-    """d_loss * d loss / d logits (one fused loss+gradient call with d_loss applied in the kernel), differentiable once
-    more (Hessian w.r.t. logits)."""
+    """d_loss * d loss / d logits, differentiable once more (Hessian w.r.t. logits).  `unit_grad` is the
+    gradient for d_loss = 1 when the forward pass already produced it (eager schedule), else None: the fused
+    loss+gradient call runs here with d_loss applied in the kernel."""
 
     @staticmethod
-    def forward(ctx, logits, d_loss, desc, aux):
+    def forward(ctx, logits, d_loss, unit_grad, desc, aux):
         ctx.desc, ctx.aux = desc, aux
         ctx.save_for_backward(logits, d_loss)
         labels, label_length, logit_length = aux
+        if unit_grad is not None:
+            dl = d_loss.to(unit_grad.dtype)
+            return (dl[None, :, None] if desc.flags & _lib.TIME_MAJOR else dl[:, None, None]) * unit_grad
         dl = d_loss.detach().to(torch.float32).contiguous()
         _, grad, _ = _lib.loss_grad(desc, logits.detach().contiguous(), labels, label_length, logit_length, d_loss=dl)
         return grad
@@ -264,7 +284,7 @@ class _FusedGradFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:      # the cotangent of d_loss: <v, d loss / d logits> per utterance
             _, grad, _ = _lib.loss_grad(ctx.desc, x, labels, label_length, logit_length)
             d_d_loss = (v.float() * grad.float()).sum(dim=(0, 2) if time_major else (1, 2))
-        return d_logits, d_d_loss, None, None
+        return d_logits, d_d_loss, None, None, None
 
 
 def ctc_loss(labels, logits, label_length, logit_length, blank_index, ctc_loss_data_cls,

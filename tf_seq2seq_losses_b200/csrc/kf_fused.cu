@@ -5,7 +5,7 @@ namespace ctcb200 {
 
 // Developer / test hook (ctcb200_debug_fused_plan in ctc_b200.h): a process-wide override of the plan below.
 static int g_plan_override[5] = {0, 0, 0, 0, 0};     // W, SL, XA, R, mode; W == 0: no override
-void fused_set_plan_override(int W, int SL, int XA, int R, int mode) {     // mode: bit 0 split, bit 1 no HALF scratch
+void fused_set_plan_override(int W, int SL, int XA, int R, int mode) {     // mode: bit 0 split, 1 no HALF scratch, 2 no idle warps
   const int v[5] = {W, SL, XA, R, mode};
   for (int i = 4; i >= 0; --i) __atomic_store_n(&g_plan_override[i], v[i], __ATOMIC_RELEASE);   // W last
 }
@@ -96,6 +96,7 @@ cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss
   a.tma = ((p.V & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0) ? 1 : 0;
   if (p.logits_bf16 && (!a.tma || (p.V & 7) != 0)) return cudaErrorInvalidValue;    // checked by the caller (api.cu)
   fused_pick(p, a.tma != 0, &a.W, &a.SL, &a.XA, &a.R, &a.split, &a.half);
+  a.rec_alone = (a.split && !(g_plan_override[0] > 0 && (g_plan_override[4] & 4))) ? 1 : 0;     // mode bit 2: off
   (void)W;
   const bool classic = p.variant == CTCB200_CLASSIC;
   if (p.logits_bf16) return classic ? launch_fused_variant<true, true, true>(a, st) : launch_fused_variant<false, true, true>(a, st);

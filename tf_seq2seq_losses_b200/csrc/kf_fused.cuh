@@ -363,6 +363,7 @@ struct FusedArgs {
   float* grad;          // [B,T,V]
   int W, SL, XA, R;
   int half;             // 1: HALF state scratch (see fused_layout)
+  int rec_alone;        // split mode: leave the warps that share the recursion warp's scheduler idle
   int split;            // 1: a cluster of two CTAs per utterance, one per side (small batches); 0: one CTA per utterance
   int tma;              // 1: rows move by 1-D TMA (V % 4 == 0, 16-byte aligned bases); 0: by 4-byte cp.async / plain stores
   long long* dbg;       // [B][warps][12] when built with CTCB200_FUSED_TIMING, else unused
@@ -1016,7 +1017,10 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
   // recursion warps on the highest warp ids, on one scheduler, or rotated by the CTA index so co-resident CTAs do not
   // stack roles): none beat this one (simplified +-1 %, classic 3-8 % slower).  In split mode the side is the CTA's rank
   // in its cluster.
-  const int side = SPLIT ? (int)(blockIdx.x & 1u) : warp / (W + 1), role = SPLIT ? warp : warp % (W + 1);
+  // Split mode with `rec_alone`: warps 4, 8, ... (which share the recursion warp's scheduler) stay idle, so the T-step
+  // chain of warp 0 has an issue port to itself; role -1 = idle (takes part in the barriers only).
+  const int side = SPLIT ? (int)(blockIdx.x & 1u) : warp / (W + 1);
+  const int role = !SPLIT ? warp % (W + 1) : !a.rec_alone ? warp : (warp == 0) ? 0 : ((warp & 3) == 0) ? -1 : warp - (warp >> 2);
   const int my = SPLIT ? 0 : side;        // index of this side's block in THIS CTA's shared memory
   const int L = utt_label_len(p, b), n_t = utt_frames(p, b), M = n_t >> 1;
   const float dl = a.d_loss ? a.d_loss[b] : 1.0f;
@@ -1197,6 +1201,8 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
           a.loss[b] = (float)ld;
         }
     }
+  } else if (role < 0) {
+    (void)middle();      // an idle warp: the CTA-wide barriers of the middle, nothing else
   } else {
     // ---- a row worker ----
 #pragma unroll 1
@@ -1274,7 +1280,10 @@ static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
     if constexpr (TMA) {       // the split plan exists for TMA-movable rows only (fused_pick never asks for it otherwise)
       cudaError_t e = ensure_smem(kf_fused_split<NS, CLASSIC, TMA, BF16>, cache[1], f.total);
       if (e != cudaSuccess) return e;
-      kf_fused_split<NS, CLASSIC, TMA, BF16><<<2 * a.p.B, (a.W + 1) * kWarp, f.total, st>>>(a);
+      int warps = a.W + 1;
+      if (a.rec_alone)       // 1 recursion warp + W workers + the idle warps 4, 8, ... in between
+        for (warps = 1; warps - 1 - (warps - 1) / 4 < a.W; ++warps) {}
+      kf_fused_split<NS, CLASSIC, TMA, BF16><<<2 * a.p.B, warps * kWarp, f.total, st>>>(a);
     } else {
       return cudaErrorInvalidValue;
     }
