@@ -258,8 +258,11 @@ class _FusedGradFn(torch.autograd.Function):
         ctx.save_for_backward(logits, d_loss)
         labels, label_length, logit_length = aux
         if unit_grad is not None:
-            dl = d_loss.to(unit_grad.dtype)
-            return (dl[None, :, None] if desc.flags & _lib.TIME_MAJOR else dl[:, None, None]) * unit_grad
+            dl = d_loss.to(torch.float32)
+            dl = dl[None, :, None] if desc.flags & _lib.TIME_MAJOR else dl[:, None, None]
+            if unit_grad.dtype == torch.float32:
+                return dl * unit_grad
+            return (dl * unit_grad.to(torch.float32)).to(unit_grad.dtype)     # bf16 gradient: multiply in fp32, round once
         dl = d_loss.detach().to(torch.float32).contiguous()
         _, grad, _ = _lib.loss_grad(desc, logits.detach().contiguous(), labels, label_length, logit_length, d_loss=dl)
         return grad

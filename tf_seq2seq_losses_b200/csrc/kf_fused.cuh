@@ -772,7 +772,6 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
             row4[2 * g + 1] = v[1];
             row4[2 * (g + kWarp)] = v[2];
             row4[2 * (g + kWarp) + 1] = v[3];
-            __syncwarp();
           }
           for (; g - lane < n8; g += kWarp) {      // warp-uniform trip count (the barriers inside need every lane)
             float4 v0, v1;
@@ -782,8 +781,8 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
               row4[2 * g] = fin(v0);
               row4[2 * g + 1] = fin(v1);
             }
-            __syncwarp();
           }
+          __syncwarp();
         } else {
           int c4 = lane;
           for (; c4 + 3 * kWarp < n4; c4 += 4 * kWarp) {
