@@ -16,10 +16,11 @@ constexpr int kNumSms = 148;
 
 // (workers per side, row buffers per worker, extra phase-A buffer, ring depth, split) for this problem; W == 0 when the
 // fused kernel cannot take it.
-//   B > 74   one CTA per utterance, both sides inside (W <= 4): prefer plans that leave room for two CTAs per SM.
+//   B > 148  one CTA per utterance, both sides inside (W <= 4): prefer plans that leave room for two CTAs per SM.
 //   B <= 74  split: a cluster of two CTAs per utterance, one side each (W <= 8), every CTA with an SM to itself.  Needs
-//            TMA-movable rows (`tma_ok`).  Measured at T=1000 V=1024 L=200 (simplified): B=32 323 vs 427 us, B=64 323 vs
-//            431 us; two split CTAs sharing an SM (B=128) lose to the one-CTA plan, 640 vs 440 us.
+//            TMA-movable rows (`tma_ok`).  Measured at T=1000 V=1024 L=200 (simplified): B=32 275 vs 427 us, B=64 279 vs
+//            431 us.
+//   B <= 148 split with 6 workers per side, two CTAs per SM (see below).
 // The HALF state scratch (fused_layout) is used whenever the plan allows it and its hand-over vectors fit the budget.
 static bool fits(const Problem& p, int W, int SL, int XA, int R, int sides, int budget, int want_half, int* half) {
   for (int h = (want_half && fused_half_ok(p.S, W, R)) ? 1 : 0; h >= 0; --h)
@@ -55,6 +56,17 @@ static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, 
         return true;
       }
     }
+  }
+  // 74 < B <= 148 (the per-GPU slice of the named batch on two GPUs): still split, two CTAs per SM -- 6 workers per side
+  // (1 + 6 + 1 idle = 8 warps at 112 registers: two such CTAs fill the register file exactly).  Measured at B=128
+  // (simplified, T=1000 V=1024 L=200): 371 us against 464 us for the one-CTA plan, 440 us for split W=4, 611 us for W=8.
+  if (tma_ok && p.B <= kNumSms && p.NS <= 8) {
+    static const int hcand[5][4] = {{6, 2, 1, 12}, {6, 2, 0, 12}, {4, 3, 1, 8}, {4, 2, 1, 8}, {4, 2, 0, 8}};
+    for (int c = 0; c < 5; ++c)
+      if (fits(p, hcand[c][0], hcand[c][1], hcand[c][2], hcand[c][3], 1, kSmemHalfSm, want_half, half)) {
+        *W = hcand[c][0]; *SL = hcand[c][1]; *XA = hcand[c][2]; *R = hcand[c][3]; *split = 1;
+        return true;
+      }
   }
   // {workers per side, row buffers per worker, extra phase-A row buffer, ring depth}.  Measured on B200 (B=256 T=1000
   // V=1024): 4 workers beat 3 for both variants; the classic variant (two state planes) only fits 4 workers next to a
