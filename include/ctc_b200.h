@@ -78,7 +78,7 @@ extern "C" {
  * serves the shape this is about a third of CTCB200_WS_LOSS_GRAD (no gathered rows, one state tensor instead of two);
  * otherwise the two are equal.  A workspace sized with CTCB200_WS_LOSS_GRAD is always accepted as well.
  * NOTE: this size is NOT monotonic in B -- the kernel choice depends on the batch size (narrow vocabularies, V < 64, take
- * the fused kernel from 80 utterances on and the larger staged scratch below that), so a caller that sizes one workspace
+ * the fused kernel from 48 utterances on and the larger staged scratch below that), so a caller that sizes one workspace
  * for its largest batch and then passes smaller batches must size with CTCB200_WS_LOSS_GRAD, or take the maximum over the
  * batch sizes it will use (ctcb200_host_create does the latter for its tail slice). */
 #define CTCB200_WS_LOSS_GRAD_LOGITS 3

@@ -68,7 +68,7 @@ def test_error_strings_and_descriptor_validation():
 def test_workspace_classes_and_kernel_choice():
     """Workspace sizing rules of include/ctc_b200.h (no kernel is launched): the training call's class is never larger
     than the general one and shrinks when the fused kernel serves the shape; ctcb200_stage_names reports the device path
-    (fused from V >= 64, or from 80 utterances on for narrower vocabularies, unless forced)."""
+    (fused from V >= 64, or from 48 utterances on for narrower vocabularies, unless forced)."""
     lib = _lib.load()
     ws = lambda d, w: lib.ctcb200_workspace_bytes(ctypes.byref(d), w)
     names = lambda d: lib.ctcb200_stage_names(ctypes.byref(d)).decode()

@@ -194,7 +194,7 @@ def test_loss_and_gradient_match_oracle(shape, variant, kernel_path):
 
 @pytest.mark.parametrize("variant", [CLASSIC, SIMPLIFIED])
 def test_narrow_vocabulary_large_batch_takes_the_fused_kernel(variant):
-    """Character-sized vocabularies are served by the staged kernels in small batches and by the fused kernel from 80
+    """Character-sized vocabularies are served by the staged kernels in small batches and by the fused kernel from 48
     utterances on (csrc/api.cu: fused_workers); both choices, unforced, against the oracle -- V = 29 rows are not 16-byte
     aligned (cp.async row mover), V = 32 rows are (TMA)."""
     import ctypes
@@ -790,13 +790,17 @@ def test_host_buffer_entry_point_matches_device_entry_point():
 
 
 def test_host_buffer_entry_point_uneven_tail_of_a_narrow_vocabulary():
-    """The training-call workspace is not monotonic in the batch size: with V < 64 a full slice of 81 utterances takes the
-    fused kernel (small scratch) while the 79-utterance tail takes the staged kernels (three times larger).  The host
+    """The training-call workspace is not monotonic in the batch size: with V < 64 a full slice of 49 utterances takes the
+    fused kernel (small scratch) while the 47-utterance tail takes the staged kernels (three times larger).  The host
     context sizes its workspace for both."""
     from tf_seq2seq_losses_b200 import _lib
-    B, T, V, L = 241, 30, 32, 8
+    B, T, V, L = 145, 30, 32, 8
     logits, labels, ll, tl = random_inputs(B, T, V, L, seed=10)
-    ctx = _lib.HostContext(B, T, V, L, 0, CLASSIC, L + 1, device=0, num_slices=3)      # slices of 81, 81, 79
+    ctx = _lib.HostContext(B, T, V, L, 0, CLASSIC, L + 1, device=0, num_slices=3)      # slices of 49, 49, 47
+    lib, d = _lib.load(), lambda b: _lib.Desc(b, T, V, L, 0, CLASSIC, L + 1, 0)
+    import ctypes
+    assert lib.ctcb200_workspace_bytes(ctypes.byref(d(47)), _lib.WS_LOSS_GRAD_LOGITS) > \
+        lib.ctcb200_workspace_bytes(ctypes.byref(d(49)), _lib.WS_LOSS_GRAD_LOGITS)
     pin = lambda a: torch.as_tensor(a).pin_memory()
     loss_h = torch.empty((B,), dtype=torch.float32).pin_memory()
     grad_h = torch.empty((B, T, V), dtype=torch.float32).pin_memory()

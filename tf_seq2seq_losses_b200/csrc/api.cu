@@ -84,10 +84,11 @@ static int fused_workers(const ctcb200_desc* desc, const Problem& p) {
   if (desc->flags & CTCB200_FORCE_STAGED) return 0;
   if (p.logits_bf16) return fused_pick_workers(p);      // bf16 rows exist in the fused kernel only
   // Narrow vocabularies (character models, V < 64) in SMALL batches are latency-bound on the T-step chain rather than on
-  // row traffic; there the staged recursion kernel, which streams the compact gathered rows, is faster (B=32 T=500 V=29:
-  // 183 us staged vs 232 us fused).  From about 80 utterances on the fused kernel wins again because the staged gradient
-  // writer grows with B while the fused kernel still fits one wave (B=256 T=255 V=32: 136 us fused vs 257 us staged).
-  if (p.V < 64 && p.B < 80 && !(desc->flags & CTCB200_FORCE_FUSED)) return 0;
+  // row traffic; there the staged recursion kernel, which streams the compact gathered rows, is as fast or faster
+  // (classic T=500 V=29 L=100, B=32: 165 us staged vs 171 us fused with the split plan).  From about 48 utterances on the
+  // fused kernel wins because the staged kernels grow with B while the fused one still fits one wave (same shape, B=64:
+  // 171 vs 201 us, B=128: 189 vs 277 us; B=256 T=255 V=32: 125 vs 228 us).
+  if (p.V < 64 && p.B < 48 && !(desc->flags & CTCB200_FORCE_FUSED)) return 0;
   return fused_pick_workers(p);
 }
 

@@ -17,8 +17,7 @@ constexpr int kNumSms = 148;
 // (workers per side, row buffers per worker, extra phase-A buffer, ring depth, split) for this problem; W == 0 when the
 // fused kernel cannot take it.
 //   B > 148  one CTA per utterance, both sides inside (W <= 4): prefer plans that leave room for two CTAs per SM.
-//   B <= 74  split: a cluster of two CTAs per utterance, one side each (W <= 8), every CTA with an SM to itself.  Needs
-//            TMA-movable rows (`tma_ok`).  Measured at T=1000 V=1024 L=200 (simplified): B=32 275 vs 427 us, B=64 279 vs
+//   B <= 74  split: a cluster of two CTAs per utterance, one side each (W <= 8), every CTA with an SM to itself.  Measured at T=1000 V=1024 L=200 (simplified): B=32 275 vs 427 us, B=64 279 vs
 //            431 us.
 //   B <= 148 split with 6 workers per side, two CTAs per SM (see below).
 // The HALF state scratch (fused_layout) is used whenever the plan allows it and its hand-over vectors fit the budget.
@@ -31,7 +30,7 @@ static bool fits(const Problem& p, int W, int SL, int XA, int R, int sides, int 
   return false;
 }
 
-static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, int* R, int* split, int* half) {
+static bool fused_pick(const Problem& p, int* W, int* SL, int* XA, int* R, int* split, int* half) {
   *W = 0; *SL = 0; *XA = 0; *R = 0; *split = 0; *half = 0;
   if (p.NS > kMaxNS) return false;
   const int ow = __atomic_load_n(&g_plan_override[0], __ATOMIC_ACQUIRE);
@@ -39,12 +38,12 @@ static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, 
   if (ow > 0) {
     const int sl = g_plan_override[1], xa = g_plan_override[2], r = g_plan_override[3], sp = mode & 1;
     if (ow <= (sp ? (p.NS > 8 ? 6 : kMaxWorkersSplit) : kMaxWorkers) && sl >= 2 && sl <= 3 && xa >= 0 && xa <= 1 && r >= 1 && r <= 2 * ow &&
-        (!sp || tma_ok) && fits(p, ow, sl, xa, r, sp ? 1 : 2, kSmemPerSm, want_half, half)) {
+        fits(p, ow, sl, xa, r, sp ? 1 : 2, kSmemPerSm, want_half, half)) {
       *W = ow; *SL = sl; *XA = xa; *R = r; *split = sp;
       return true;
     }
   }
-  if (tma_ok && 2 * p.B <= kNumSms) {
+  if (2 * p.B <= kNumSms) {
     static const int scand[8][4] = {{8, 3, 1, 16}, {8, 2, 1, 16}, {8, 2, 0, 16}, {6, 3, 1, 12}, {6, 2, 1, 12}, {6, 2, 0, 12},
                                     {4, 3, 1, 8}, {4, 2, 0, 8}};
     for (int c = 0; c < 8; ++c) {
@@ -60,7 +59,7 @@ static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, 
   // 74 < B <= 148 (the per-GPU slice of the named batch on two GPUs): still split, two CTAs per SM -- 6 workers per side
   // (1 + 6 + 1 idle = 8 warps at 112 registers: two such CTAs fill the register file exactly).  Measured at B=128
   // (simplified, T=1000 V=1024 L=200): 371 us against 464 us for the one-CTA plan, 440 us for split W=4, 611 us for W=8.
-  if (tma_ok && p.B <= kNumSms && p.NS <= 8) {
+  if (p.B <= kNumSms && p.NS <= 8) {
     static const int hcand[5][4] = {{6, 2, 1, 12}, {6, 2, 0, 12}, {4, 3, 1, 8}, {4, 2, 1, 8}, {4, 2, 0, 8}};
     for (int c = 0; c < 5; ++c)
       if (fits(p, hcand[c][0], hcand[c][1], hcand[c][2], hcand[c][3], 1, kSmemHalfSm, want_half, half)) {
@@ -86,7 +85,7 @@ static bool fused_pick(const Problem& p, bool tma_ok, int* W, int* SL, int* XA, 
 
 int fused_pick_workers(const Problem& p) {
   int W, SL, XA, R, split, half;
-  fused_pick(p, false, &W, &SL, &XA, &R, &split, &half);     // eligibility does not depend on the row mover
+  fused_pick(p, &W, &SL, &XA, &R, &split, &half);
   return W;
 }
 
@@ -107,7 +106,7 @@ cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss
 #endif
   a.tma = ((p.V & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0) ? 1 : 0;
   if (p.logits_bf16 && (!a.tma || (p.V & 7) != 0)) return cudaErrorInvalidValue;    // checked by the caller (api.cu)
-  fused_pick(p, a.tma != 0, &a.W, &a.SL, &a.XA, &a.R, &a.split, &a.half);
+  fused_pick(p, &a.W, &a.SL, &a.XA, &a.R, &a.split, &a.half);
   a.rec_alone = (a.split && !(g_plan_override[0] > 0 && (g_plan_override[4] & 4))) ? 1 : 0;     // mode bit 2: off
   (void)W;
   const bool classic = p.variant == CTCB200_CLASSIC;

@@ -1276,16 +1276,12 @@ static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
   // never lowered, so the launch below always finds at least f.total bytes allowed.
   static int cache[2][kMaxDevices];
   if (a.split) {
-    if constexpr (TMA) {       // the split plan exists for TMA-movable rows only (fused_pick never asks for it otherwise)
-      cudaError_t e = ensure_smem(kf_fused_split<NS, CLASSIC, TMA, BF16>, cache[1], f.total);
-      if (e != cudaSuccess) return e;
-      int warps = a.W + 1;
-      if (a.rec_alone)       // 1 recursion warp + W workers + the idle warps 4, 8, ... in between
-        for (warps = 1; warps - 1 - (warps - 1) / 4 < a.W; ++warps) {}
-      kf_fused_split<NS, CLASSIC, TMA, BF16><<<2 * a.p.B, warps * kWarp, f.total, st>>>(a);
-    } else {
-      return cudaErrorInvalidValue;
-    }
+    cudaError_t e = ensure_smem(kf_fused_split<NS, CLASSIC, TMA, BF16>, cache[1], f.total);
+    if (e != cudaSuccess) return e;
+    int warps = a.W + 1;
+    if (a.rec_alone)       // 1 recursion warp + W workers + the idle warps 4, 8, ... in between
+      for (warps = 1; warps - 1 - (warps - 1) / 4 < a.W; ++warps) {}
+    kf_fused_split<NS, CLASSIC, TMA, BF16><<<2 * a.p.B, warps * kWarp, f.total, st>>>(a);
   } else {
     cudaError_t e = ensure_smem(kf_fused<NS, CLASSIC, TMA, BF16>, cache[0], f.total);
     if (e != cudaSuccess) return e;
@@ -1294,12 +1290,8 @@ static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
   const cudaError_t err = cudaGetLastError();
   if (err == cudaErrorLaunchOutOfResources) {      // say which resource: the plan and the compiled kernel disagree
     cudaFuncAttributes fa{};
-    if constexpr (TMA) {
-      if (a.split) (void)cudaFuncGetAttributes(&fa, kf_fused_split<NS, CLASSIC, TMA, BF16>);
-      else (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA, BF16>);
-    } else {
-      (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA, BF16>);
-    }
+    if (a.split) (void)cudaFuncGetAttributes(&fa, kf_fused_split<NS, CLASSIC, TMA, BF16>);
+    else (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA, BF16>);
     fprintf(stderr, "libctc_b200: kf_fused%s<NS=%d,classic=%d,tma=%d> bf16=%d W=%d SL=%d XA=%d R=%d: %d threads, %d B dynamic smem; kernel: %d regs, "
             "max %d threads/block, %zu B static smem, %d B max dynamic smem, %zu B local\n", a.split ? "_split" : "", NS, (int)CLASSIC,
             (int)TMA, (int)BF16, a.W, a.SL, a.XA, a.R, (a.split ? 1 : 2) * (a.W + 1) * kWarp, f.total, fa.numRegs, fa.maxThreadsPerBlock,
