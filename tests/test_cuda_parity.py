@@ -370,7 +370,7 @@ def test_cuda_graph_capture_and_replay(variant, schedule, monkeypatch):
 def test_bfloat16_logits(shape, variant):
     """CTCB200_LOGITS_BF16 (an extension; the reference asserts float32, base_loss.py:131): the kernels read bfloat16 rows,
     widen them on the fly and compute in fp32, so the result is the oracle's on the bf16-ROUNDED inputs -- loss and
-    float32 gradient to the usual fp32 tolerance, the bfloat16 gradient to half a bf16 ulp on top."""
+    float32 gradient to the usual fp32 tolerance, the bfloat16 gradient to its roundings on top."""
     from tf_seq2seq_losses_b200 import _lib
     B, T, V, L = shape
     logits, labels, ll, tl = random_inputs(B, T, V, L, seed=B + T)
@@ -399,7 +399,9 @@ def test_bfloat16_logits(shape, variant):
     assert x.grad.dtype == torch.bfloat16
     want_w = want_grad * w[:, None, None]
     got = x.grad.float().cpu().numpy()
-    assert np.max(np.abs(got - want_w) - np.abs(want_w) * 2.0 ** -8) <= 2.5 * atol
+    # bfloat16 keeps 8 significant bits: one rounding is a relative 2^-8; the small-shape (eager) schedule rounds the unit
+    # gradient in the kernel and the d_loss-weighted product once more
+    assert np.max(np.abs(got - want_w) - np.abs(want_w) * 2.0 ** -7) <= 2.5 * atol
     # shapes the fused kernel cannot take are refused, not silently converted
     bad = _cuda(logits[:, :, :V - 4]).to(torch.bfloat16).contiguous()
     with pytest.raises(_lib.CtcB200Error):

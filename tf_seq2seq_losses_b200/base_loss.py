@@ -46,6 +46,8 @@ def _max_label_length_plus_one(label_length: torch.Tensor, max_label_length: Opt
         captured, where the bound labels.shape[1] + 1 is used instead.
     """
     if max_label_length is not None:
+        if not label_length.is_cuda and label_length.numel() > 0:      # free to check on the host: refuse to truncate labels
+            assert int(label_length.max()) <= int(max_label_length), "max_label_length is smaller than max(label_length)"
         return int(max_label_length) + 1
     if label_length.numel() == 0:
         return 1
