@@ -439,7 +439,7 @@ def main():
         os.sched_setaffinity(0, affinity_before)      # the CPU baseline below uses every host core
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU leg is an N=1 report (the reference arm re-times it at every N)
         nb = min(local_B, args.cpu_sample)
         v, dt, cores = cpu_port_samples_per_s(1 if variant == "simplified" else 0, logits_h[:nb].float(), labels_h[:nb], ll_h[:nb], tl_h[:nb], 2)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",

@@ -1018,6 +1018,9 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
   // in its cluster.
   // Split mode with `rec_alone`: warps 4, 8, ... (which share the recursion warp's scheduler) stay idle, so the T-step
   // chain of warp 0 has an issue port to itself; role -1 = idle (takes part in the barriers only).
+  // (For the small one-CTA plans of wide rows -- W = 1 or 2, two CTAs per SM -- shifting the roles of second-wave CTAs by
+  // one warp, so that recursion warps and workers of co-resident CTAs do not meet on the same scheduler, was measured at
+  // V = 5000: 5.41 ms against 5.06 ms without.  Not done.)
   const int side = SPLIT ? (int)(blockIdx.x & 1u) : warp / (W + 1);
   const int role = !SPLIT ? warp % (W + 1) : !a.rec_alone ? warp : (warp == 0) ? 0 : ((warp & 3) == 0) ? -1 : warp - (warp >> 2);
   const int my = SPLIT ? 0 : side;        // index of this side's block in THIS CTA's shared memory
@@ -1135,7 +1138,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
     if (a.grad == nullptr) {
       // Loss-only call (the forward pass of a training step, or evaluation): -log Z is known at the middle, so the call
       // costs phase A alone -- half the chain, one read of the logits, nothing written but the loss.
-      if (side == 0 && tid == 0) a.loss[b] = dead ? INFINITY : (float)lossd_mid;
+      if (side == 0 && role == 0 && lane == 0) a.loss[b] = dead ? INFINITY : (float)lossd_mid;
       return false;
     }
     return !dead;
