@@ -41,7 +41,7 @@ def test_error_strings_and_descriptor_validation():
                 _lib.Desc(4, 10, 8, 3, 8, 0, 4, 0),       # blank out of range (V = 8)
                 _lib.Desc(4, 10, 8, 3, 0, 2, 4, 0),       # unknown variant
                 _lib.Desc(4, 10, 8, 3, 0, 0, 4, 1 << 20),  # unknown flag
-                _lib.Desc(4, 1000, 8, 600, 0, 0, 601, 0),  # more than 512 label states
+                _lib.Desc(4, 1200, 8, 1100, 0, 0, 1101, 0),  # more than 1024 label states
                 _lib.Desc(4, 10, 40000, 3, 0, 0, 4, 0)):   # more than 32768 tokens
         assert lib.ctcb200_workspace_bytes(ctypes.byref(bad), _lib.WS_LOSS_GRAD) == 0
     # null pointers and a too-small workspace are reported, not dereferenced

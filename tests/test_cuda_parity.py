@@ -766,9 +766,9 @@ def test_no_cpu_fallback_and_size_limits():
     with pytest.raises(_lib.CtcB200Error):
         pkg.classic_ctc_loss(torch.ones((1, 2), dtype=torch.int32), torch.zeros((1, 4, 3)), torch.tensor([2]),
                              torch.tensor([4]), 0)
-    with pytest.raises(_lib.CtcB200Error):   # 600 label states > 512
-        pkg.classic_ctc_loss(torch.ones((1, 600), dtype=torch.int32).cuda(), torch.zeros((1, 700, 3)).cuda(),
-                             torch.tensor([599]).cuda(), torch.tensor([700]).cuda(), 0)
+    with pytest.raises(_lib.CtcB200Error):   # 1100 label states > 1024
+        pkg.classic_ctc_loss(torch.ones((1, 1100), dtype=torch.int32).cuda(), torch.zeros((1, 1200, 3)).cuda(),
+                             torch.tensor([1099]).cuda(), torch.tensor([1200]).cuda(), 0)
     with pytest.raises(AssertionError):      # base_loss.py:129-138
         pkg.classic_ctc_loss(torch.ones((2, 2), dtype=torch.int32).cuda(), torch.zeros((1, 4, 3)).cuda(),
                              torch.tensor([2]).cuda(), torch.tensor([4]).cuda(), 0)
@@ -918,8 +918,9 @@ def test_fused_worker_configurations(cfg, variant):
 
 
 def test_size_limits_both_paths():
-    """The largest supported label-state count (U = 512 -> 16 states per lane) on both device paths, and a vocabulary
-    whose rows do not fit the fused kernel's shared-memory plan (V = 32768 -> staged kernels by construction)."""
+    """The largest label-state count the fused kernel carries (U = 512 -> 16 states per lane) on both device paths, the
+    staged kernels beyond it (U = 640 -> 20 per lane, U = 1024 -> 32 per lane, both variants), and a vocabulary whose
+    rows do not fit the fused kernel's shared-memory plan (V = 32768 -> staged kernels by construction)."""
     from oracle import c_oracle
     from tf_seq2seq_losses_b200 import _lib
     B, T, V, L = 2, 560, 64, 511
@@ -937,6 +938,18 @@ def test_size_limits_both_paths():
             assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= GRAD_ATOL_LONG
     finally:
         _lib.DEFAULT_FLAGS = old
+    for (T, L, variant, seed) in ((700, 639, SIMPLIFIED, 19), (1100, 1023, CLASSIC, 20), (1100, 1023, SIMPLIFIED, 21)):
+        B, V = 2, 48
+        logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed, ragged=False)
+        ll[1], tl[1] = L - 300, T - 200
+        want_loss, want_grad = c_oracle.loss_grad(labels, logits, ll, tl, 0, variant)
+        assert _lib.kernel_plan(_lib.make_desc(B, T, V, L, 0, variant, L + 1)) != "kf_fused"
+        x = _cuda(logits).requires_grad_(True)
+        fn = _pkg().classic_ctc_loss if variant == CLASSIC else _pkg().simple_ctc_loss
+        loss = fn(_cuda(labels), x, _cuda(ll), _cuda(tl), 0)
+        loss.sum().backward()
+        _loss_close(loss.detach().cpu().numpy(), want_loss)
+        assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= GRAD_ATOL_LONG
     B, T, V, L = 2, 40, 32768, 10
     logits, labels, ll, tl = random_inputs(B, T, V, L, seed=18)
     want_loss, want_grad = c_oracle.loss_grad(labels, logits, ll, tl, 0, SIMPLIFIED)

@@ -20,7 +20,8 @@ static int make_problem(const ctcb200_desc* d, Problem* p) {
   p->B = d->B; p->T = d->T; p->V = d->V; p->Lw = d->Lw; p->blank = d->blank; p->variant = d->variant;
   p->U = d->U > 0 ? d->U : d->Lw + 1;
   p->NS = (p->U + kWarp - 1) / kWarp;
-  if (p->NS > kMaxNS || d->V > kMaxV) return CTCB200_ERR_UNSUPPORTED_SIZE;
+  if (p->NS > kMaxNS) p->NS = (p->NS + 3) & ~3;      // staged kernels only: instantiated in steps of four states per lane
+  if (p->NS > kMaxNSStaged || d->V > kMaxV) return CTCB200_ERR_UNSUPPORTED_SIZE;
   if ((long long)d->B * (long long)(d->T + 1) > (1LL << 40)) return CTCB200_ERR_UNSUPPORTED_SIZE;
   p->Upad = p->NS * kWarp;
   p->S = d->variant == CTCB200_CLASSIC ? 2 : 1;
@@ -146,7 +147,7 @@ const char* ctcb200_strerror(int code) {
     case CTCB200_ERR_NULL_POINTER: return "null pointer";
     case CTCB200_ERR_BAD_DESCRIPTOR: return "bad descriptor";
     case CTCB200_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
-    case CTCB200_ERR_UNSUPPORTED_SIZE: return "unsupported size (U > 512 states, V > 32768 tokens, or bf16 rows the fused kernel cannot take)";
+    case CTCB200_ERR_UNSUPPORTED_SIZE: return "unsupported size (U > 1024 states, V > 32768 tokens, or bf16 rows the fused kernel cannot take)";
     case CTCB200_ERR_CUDA: return "CUDA launch failure";
     case CTCB200_ERR_MISALIGNED: return "workspace must be 256-byte aligned";
     default: return "unknown error";

@@ -15,7 +15,8 @@ namespace ctcb200 {
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kMaxNS = 16;          // states per lane -> U <= 512
+constexpr int kMaxNS = 16;          // states per lane the fused kernel carries -> U <= 512
+constexpr int kMaxNSStaged = 32;    // the staged kernels go on to U <= 1024 (NS rounded up to 20, 24, 28 or 32 above 16)
 constexpr int kMaxV = 32768;        // token -> slot map lives in shared memory as int16
 #define kNegInf (-INFINITY)
 

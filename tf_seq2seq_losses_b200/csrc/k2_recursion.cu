@@ -20,7 +20,10 @@
 namespace ctcb200 {
 
 constexpr int kGroup = 4;      // frames per unrolled group (the renormalisation cadence)
-constexpr int kStages = 16;    // cp.async ring depth: frames in flight per warp (DRAM latency / step time)
+// cp.async ring depth: frames in flight per warp (DRAM latency / step time).  The wide state vectors beyond the fused
+// kernel's range (NS > 16, 4 KB frames and a longer step) take half the depth, which keeps the ring under 48 KB.
+template <int NS>
+struct K2Stages { static constexpr int value = NS > 16 ? 8 : 16; };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -75,6 +78,7 @@ __global__ void __launch_bounds__(kWarp) k2_recursion(Problem p, Scratch s, floa
   LabelBits<NS> lb;
   if (CLASSIC) lb = make_label_bits<NS>(p, b, L, lane);
   extern __shared__ __align__(16) float ring[];
+  constexpr int kStages = K2Stages<NS>::value;
 
   if (blockIdx.y == 0) {
     // ------------------------------------------------ alpha: t = 0 .. n_t-1 ----------------------------------
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(kWarp) k2_recursion(Problem p, Scratch s, floa
 template <int NS>
 static cudaError_t launch_ns(const Problem& p, const Scratch& s, float* loss, bool full, cudaStream_t st) {
   dim3 grid(p.B, 2);
-  const size_t smem = (size_t)kStages * (p.Upad + 4) * sizeof(float);     // <= 33 KB
+  const size_t smem = (size_t)K2Stages<NS>::value * (p.Upad + 4) * sizeof(float);     // <= 33 KB
   if (p.variant == CTCB200_CLASSIC) k2_recursion<NS, true><<<grid, kWarp, smem, st>>>(p, s, loss, full);
   else k2_recursion<NS, false><<<grid, kWarp, smem, st>>>(p, s, loss, full);
   return cudaGetLastError();
@@ -203,6 +207,7 @@ cudaError_t launch_recursion(const Problem& p, const Scratch& s, float* loss, bo
     CTCB200_CASE(1) CTCB200_CASE(2) CTCB200_CASE(3) CTCB200_CASE(4) CTCB200_CASE(5) CTCB200_CASE(6)
     CTCB200_CASE(7) CTCB200_CASE(8) CTCB200_CASE(9) CTCB200_CASE(10) CTCB200_CASE(11) CTCB200_CASE(12)
     CTCB200_CASE(13) CTCB200_CASE(14) CTCB200_CASE(15) CTCB200_CASE(16)
+    CTCB200_CASE(20) CTCB200_CASE(24) CTCB200_CASE(28) CTCB200_CASE(32)      // U > 512: make_problem rounds NS up
 #undef CTCB200_CASE
     default:
       return cudaErrorInvalidValue;

@@ -212,6 +212,7 @@ cudaError_t launch_log_grad(const Problem& p, const Scratch& s, float* log_grad,
     CTCB200_CASE(1) CTCB200_CASE(2) CTCB200_CASE(3) CTCB200_CASE(4) CTCB200_CASE(5) CTCB200_CASE(6)
     CTCB200_CASE(7) CTCB200_CASE(8) CTCB200_CASE(9) CTCB200_CASE(10) CTCB200_CASE(11) CTCB200_CASE(12)
     CTCB200_CASE(13) CTCB200_CASE(14) CTCB200_CASE(15) CTCB200_CASE(16)
+    CTCB200_CASE(20) CTCB200_CASE(24) CTCB200_CASE(28) CTCB200_CASE(32)      // U > 512: make_problem rounds NS up
 #undef CTCB200_CASE
     default:
       return cudaErrorInvalidValue;
@@ -255,6 +256,7 @@ cudaError_t launch_grad(const Problem& p, const Scratch& s, const float* d_loss,
     CTCB200_CASE(1) CTCB200_CASE(2) CTCB200_CASE(3) CTCB200_CASE(4) CTCB200_CASE(5) CTCB200_CASE(6)
     CTCB200_CASE(7) CTCB200_CASE(8) CTCB200_CASE(9) CTCB200_CASE(10) CTCB200_CASE(11) CTCB200_CASE(12)
     CTCB200_CASE(13) CTCB200_CASE(14) CTCB200_CASE(15) CTCB200_CASE(16)
+    CTCB200_CASE(20) CTCB200_CASE(24) CTCB200_CASE(28) CTCB200_CASE(32)      // U > 512: make_problem rounds NS up
 #undef CTCB200_CASE
     default:
       return cudaErrorInvalidValue;

@@ -1138,7 +1138,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
     if (a.grad == nullptr) {
       // Loss-only call (the forward pass of a training step, or evaluation): -log Z is known at the middle, so the call
       // costs phase A alone -- half the chain, one read of the logits, nothing written but the loss.
-      if (side == 0 && role == 0 && lane == 0) a.loss[b] = dead ? INFINITY : (float)lossd_mid;
+      if (side == 0 && tid == 0) a.loss[b] = dead ? INFINITY : (float)lossd_mid;
       return false;
     }
     return !dead;
