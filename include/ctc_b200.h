@@ -66,7 +66,7 @@ extern "C" {
 #define CTCB200_ERR_NULL_POINTER (-1)
 #define CTCB200_ERR_BAD_DESCRIPTOR (-2)
 #define CTCB200_ERR_WORKSPACE_TOO_SMALL (-3)
-#define CTCB200_ERR_UNSUPPORTED_SIZE (-4) /* U > 512 states or V > 32768 tokens */
+#define CTCB200_ERR_UNSUPPORTED_SIZE (-4) /* U > 1024 states (512 for bf16 rows) or V > 32768 tokens */
 #define CTCB200_ERR_CUDA (-5)             /* launch failure; cudaGetLastError() was consumed */
 #define CTCB200_ERR_MISALIGNED (-6)       /* workspace not 256-byte aligned */
 

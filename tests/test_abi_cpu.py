@@ -85,6 +85,11 @@ def test_workspace_classes_and_kernel_choice():
     big_char = _lib.Desc(256, 255, 32, 255, 0, _lib.CLASSIC, 127, 0)         # the reference's tests/benchmark.py shape
     assert names(small_char).startswith("k1_") and names(big_char) == "kf_fused"
     assert names(_lib.Desc(32, 500, 29, 100, 0, _lib.CLASSIC, 101, _lib.FORCE_FUSED)) == "kf_fused"
+    # beyond the fused kernel's 512 label states the staged kernels serve the call (up to 1024), bf16 rows do not exist
+    wide = _lib.Desc(8, 1100, 1024, 1023, 0, _lib.CLASSIC, 1024, 0)
+    assert names(wide) == "k1_softmax_gather,k2_recursion,k3_grad" and ws(wide, _lib.WS_LOSS_GRAD_LOGITS) > 0
+    assert names(_lib.Desc(8, 1100, 1024, 1023, 0, _lib.CLASSIC, 1024, _lib.FORCE_FUSED)).startswith("k1_")
+    assert names(_lib.Desc(8, 600, 1024, 512, 0, _lib.CLASSIC, 512, 0)) == "kf_fused"
     time_major = _lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, _lib.TIME_MAJOR)
     assert ws(time_major, _lib.WS_LOSS_GRAD_LOGITS) == ws(north_star, _lib.WS_LOSS_GRAD_LOGITS)      # scratch keeps its layout
     assert ws(_lib.Desc(256, 1000, 1024, 200, 0, _lib.SIMPLIFIED, 201, 64), _lib.WS_LOSS_GRAD) == 0     # unknown flag bit

@@ -20,7 +20,7 @@ TIME_MAJOR = 8
 LOGITS_BF16 = 16
 GRAD_BF16 = 32
 WS_LOSS_GRAD, WS_STATES, WS_HESSIAN, WS_LOSS_GRAD_LOGITS, WS_HVP_LOGITS, WS_DECODE = 0, 1, 2, 3, 4, 5
-MAX_STATES = 512
+MAX_STATES = 1024
 MAX_TOKENS = 32768
 
 _LIB_NAME = "libctc_b200.so"
