@@ -311,7 +311,8 @@ __device__ __forceinline__ void subtract_frame_occupancies(const float* a0, cons
     if (occ[j] > 0.0f) atomicAdd(&row[tok[j]], -occ[j]);
   }
   osum = warp_sum(osum);
-  if (lane == 0) atomicAdd(&row[blank], -(total - osum));
+  __syncwarp();
+  if (lane == 0) row[blank] -= total - osum;      // no state scatters into the blank column: a plain update
 }
 
 template <int NS>
@@ -338,12 +339,53 @@ __global__ void __launch_bounds__(kK4Warps * kWarp)
   const size_t TV = (size_t)p.T * p.V;
   float* slab = HVP ? nullptr : hessian + ((size_t)b * p.T + t) * p.V * TV;
   float* out_hv = HVP ? hvp_out + ((size_t)b * p.T + t) * p.V : nullptr;
+  // 128-bit zero fill of `n` floats at `dst` by `nthr` cooperating threads (scalar when the run is not 16-byte aligned)
+  auto zero_fill = [&](float* dst, size_t n, int me, int nthr) {
+    if (((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0)) {
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (size_t i = me; i < (n >> 2); i += nthr) d4[i] = z;
+    } else {
+      for (size_t i = me; i < n; i += nthr) dst[i] = 0.0f;
+    }
+  };
   if (dead) {
     if (HVP) for (int k = tid; k < p.V; k += blockDim.x) out_hv[k] = 0.0f;
-    else for (size_t i = tid; i < (size_t)p.V * TV; i += blockDim.x) slab[i] = 0.0f;
+    else zero_fill(slab, (size_t)p.V * TV, tid, blockDim.x);
     return;
   }
   float* row = reinterpret_cast<float*>(smem_raw) + (size_t)warp * p.V;
+  // Work list of the CTA.  Only the blank and the tokens of this utterance's label have non-zero second derivatives
+  // (g[t,k] == 0 and no alignment emits k otherwise); which warp got which token used to be k % 8, i.e. luck: with 13 of
+  // 32 tokens in the label, some warps propagated four chain pairs while others had none (ncu: 21 % active warps of 37.5 %
+  // resident).  Now the distinct label tokens are compacted into `list` (a bitmap over the vocabulary dedups them) and
+  // the warps draw (token, direction) items -- the longer direction of every token first, then the shorter ones, then (dense
+  // form) the zero rows of the tokens outside the label -- from a shared counter.
+  const int nW = (p.V + 31) >> 5;
+  unsigned* bitmap = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(smem_raw) + (size_t)kK4Warps * p.V);
+  int* list = reinterpret_cast<int*>(bitmap + nW);          // [kUpad + 1] distinct tokens: blank first
+  float* hvacc = reinterpret_cast<float*>(list + kUpad + 1);  // [kUpad + 1] HVP: the two directions of a token meet here
+  int* ctr = reinterpret_cast<int*>(hvacc + kUpad + 1);      // [0] list length, [1] next work item
+  for (int i = tid; i < nW; i += blockDim.x) bitmap[i] = 0u;
+  for (int i = tid; i < kUpad + 1; i += blockDim.x) hvacc[i] = 0.0f;
+  __syncthreads();
+  if (tid == 0) {
+    bitmap[p.blank >> 5] = 1u << (p.blank & 31);
+    list[0] = p.blank;
+    ctr[0] = 1;
+    ctr[1] = 0;
+  }
+  __syncthreads();
+  for (int l = tid; l < L; l += blockDim.x) {
+    const int tk = utt_token(p, b, l, L);
+    if (tk >= 0 && tk < p.V) {
+      const unsigned bit = 1u << (tk & 31);
+      if (!(atomicOr(&bitmap[tk >> 5], bit) & bit)) list[atomicAdd(&ctr[0], 1)] = tk;
+    }
+  }
+  __syncthreads();
+  const int n_lab = ctr[0];
+  if (HVP) for (int k = tid; k < p.V; k += blockDim.x) if (!((bitmap[k >> 5] >> (k & 31)) & 1u)) out_hv[k] = 0.0f;
   int tok[NS];
 #pragma unroll
   for (int j = 0; j < NS; ++j) tok[j] = utt_token(p, b, lane * NS + j, L);
@@ -382,20 +424,26 @@ __global__ void __launch_bounds__(kK4Warps * kWarp)
     __syncwarp();
   };
 
-  for (int k = warp; k < p.V; k += kK4Warps) {
-    float* hk = HVP ? nullptr : slab + (size_t)k * TV;
-    // is k the blank or one of this utterance's label tokens?
-    bool mine = false;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) mine |= (lane * NS + j < L) && (tok[j] == k);
-    const bool in_label = (k == p.blank) || __any_sync(kFull, mine);
-    if (!in_label) {             // g[t,k] == 0 and every path term vanishes
-      if (HVP) { if (lane == 0) out_hv[k] = 0.0f; }
-      else for (size_t i = lane; i < TV; i += kWarp) hk[i] = 0.0f;
+  const bool fwd_first = (n_t - 1 - t) >= t;          // the direction with more frames goes first
+  const int n_items = 2 * n_lab + (HVP ? 0 : p.V);
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&ctr[1], 1);
+    item = __shfl_sync(kFull, item, 0);
+    if (item >= n_items) break;
+    if (item >= 2 * n_lab) {       // a token outside the label: g[t,k] == 0 and every path term vanishes
+      const int kz = item - 2 * n_lab;
+      if (!((bitmap[kz >> 5] >> (kz & 31)) & 1u)) zero_fill(slab + (size_t)kz * TV, TV, lane, kWarp);
       continue;
     }
+    const int li = (item < n_lab) ? item : item - n_lab;
+    const bool fwd = (item < n_lab) == fwd_first;
+    const int k = list[li];
+    float* hk = HVP ? nullptr : slab + (size_t)k * TV;
     const float gk = g_b[(size_t)t * p.V + k];
     float hv = 0.0f;
+    float v0[NS], v1[NS];
+    if (fwd) {
     if (!HVP) for (size_t i = (size_t)n_t * p.V + lane; i < TV; i += kWarp) hk[i] = 0.0f;   // frames beyond logit_length
     // same frame: [k == k'] g[t,k] + g[t,k] g[t,k']
     {
@@ -404,7 +452,6 @@ __global__ void __launch_bounds__(kK4Warps * kWarp)
       finish_row(t, hv, hk);
     }
     // ---- later frames: push alpha[t] through "emit k", propagate forward ----
-    float v0[NS], v1[NS];
     {
       float a_left0 = __shfl_up_sync(kFull, a0t[NS - 1], 1), a_left1 = __shfl_up_sync(kFull, a1t[NS - 1], 1);
       float d_left = __shfl_up_sync(kFull, dt[NS - 1], 1);
@@ -443,6 +490,7 @@ __global__ void __launch_bounds__(kK4Warps * kWarp)
       if (CLASSIC) alpha_step_classic<NS>(v0, v1, d2, h2, lane, lb);
       else alpha_step_simplified<NS>(v0, d2, h2, lane);
     }
+    } else {
     // ---- earlier frames: pull beta[t+1] back through "emit k", propagate backward ----
     {
       float b_right1 = __shfl_down_sync(kFull, CLASSIC ? b1t[0] : b0t[0], 1);
@@ -486,17 +534,29 @@ __global__ void __launch_bounds__(kK4Warps * kWarp)
       if (CLASSIC) beta_step_classic<NS>(v0, v1, d2, h2, lane, lb);
       else beta_step_simplified<NS>(v0, d2, h2, lane);
     }
+    }
     if (HVP) {
       hv = warp_sum(hv);
-      if (lane == 0) out_hv[k] = hv;
+      if (lane == 0) atomicAdd(&hvacc[li], hv);      // two terms onto zero: the order does not matter
     }
   }
+  if (HVP) {
+    __syncthreads();
+    for (int i = tid; i < n_lab; i += blockDim.x) out_hv[list[i]] = hvacc[i];
+  }
+}
+
+// rows of the eight warps + vocabulary bitmap + token list + HVP accumulators + two counters
+template <int NS>
+static size_t k4_regs_smem_bytes(const Problem& p) {
+  return (size_t)kK4Warps * p.V * sizeof(float) + (size_t)((p.V + 31) >> 5) * sizeof(unsigned) +
+         (size_t)(NS * kWarp + 1) * (sizeof(int) + sizeof(float)) + 2 * sizeof(int);
 }
 
 template <int NS, bool CLASSIC, bool HVP>
 static cudaError_t launch_k4_regs(const Problem& p, const Scratch& s, const float* g, float* hessian,
                                   const float* d_gradient, float* hvp_out, cudaStream_t st) {
-  const size_t smem = (size_t)kK4Warps * p.V * sizeof(float);
+  const size_t smem = k4_regs_smem_bytes<NS>(p);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k4_hessian_regs<NS, CLASSIC, HVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -102,6 +102,9 @@ def readme_case(variant, name):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "hessian":      # the Hessian configuration alone
+        hessian_case(64, 50, 32, 15)
+        sys.exit(0)
     readme_case(_lib.CLASSIC, "README benchmark classic B=256 T=255 V=32")
     readme_case(_lib.SIMPLIFIED, "README benchmark simplified B=256 T=255 V=32")
     loss_grad_case("cfg1 classic B=32 T=500 V=29 L=100", 32, 500, 29, 100, _lib.CLASSIC, False)

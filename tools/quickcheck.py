@@ -12,7 +12,8 @@ from tests.ref_cases import random_inputs  # noqa: E402
 from tf_seq2seq_losses_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
-SHAPES = [(3, 6, 5, 3), (8, 64, 10, 30), (8, 20, 8, 9), (4, 33, 29, 12), (5, 61, 96, 20), (6, 200, 64, 40), (90, 40, 64, 9), (170, 14, 64, 5)]
+SHAPES = [(3, 6, 5, 3), (8, 64, 10, 30), (8, 20, 8, 9), (4, 33, 29, 12), (5, 61, 96, 20), (6, 200, 64, 40), (90, 40, 64, 9), (170, 14, 64, 5),
+          (4, 50, 132, 40), (4, 50, 130, 40), (3, 40, 256, 100), (150, 30, 128, 20)]
 PLANS = {"default": (0, 0, 0, 0, 0), "nohalf W4": (4, 2, 1, 8, 2), "half W4": (4, 2, 1, 8, 0), "W2 R4": (2, 2, 0, 4, 0),
          "split W8": (8, 3, 1, 16, 1), "split W8 nohalf": (8, 3, 1, 16, 3), "W1 R1": (1, 2, 0, 1, 0)}
 only = sys.argv[1] if len(sys.argv) > 1 else None
