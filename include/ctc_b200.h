@@ -109,9 +109,9 @@ int ctcb200_launches_per_call(const ctcb200_desc* desc);
 
 /* Developer / test hook: pins the fused kernel's plan (row workers per side, row buffers per worker, extra phase-A row
  * buffer 0/1, ring depth in frames, mode: bit 0 = split, one CTA per side in a two-CTA cluster; bit 1 = store every state
- * row instead of every second one) for every later call in this process, so a test can walk every plan on one shape;
- * plans that do not fit are ignored.  workers = 0 restores the built-in choice.  Not part of the reference-facing
- * surface. */
+ * row instead of every second one; bit 2 = no idle warps in split plans; bit 3 = no row helpers, also honoured with
+ * workers = 0) for every later call in this process, so a test can walk every plan on one shape; plans that do not fit
+ * are ignored.  workers = 0 restores the built-in choice.  Not part of the reference-facing surface. */
 void ctcb200_debug_fused_plan(int workers, int row_buffers, int extra_phase_a_buffer, int ring_depth, int mode);
 
 /* Bytes of device workspace needed by the entry point named by `what` (CTCB200_WS_*); 0 on a bad descriptor. */

@@ -917,6 +917,49 @@ def test_fused_worker_configurations(cfg, variant):
         lib.ctcb200_debug_fused_plan(0, 0, 0, 0, 0)
 
 
+@pytest.mark.parametrize("variant", [SIMPLIFIED, CLASSIC])
+@pytest.mark.parametrize("V", [2048, 2052, 3000, 5000])
+@pytest.mark.parametrize("cfg", [(0, 0, 0, 0, 0), (2, 2, 0, 4, 0), (1, 2, 0, 2, 0), (2, 2, 0, 2, 0), (0, 0, 0, 0, 8)],
+                         ids=["default", "W2", "W1", "W2_R2", "no_helpers"])
+def test_row_helpers_on_wide_rows(cfg, V, variant):
+    """Wide fp32 rows with at most two workers per side: every worker has a helper warp that reduces / exponentiates the upper
+    part of its rows (kf_fused.cuh, helper_phase).  Shapes whose helper part is exactly one chunk, one chunk and one
+    element, and several chunks with a ragged tail; ragged lengths, an infeasible sample, repeated tokens and an upstream
+    gradient (the scaled softmax pass); with mode bit 3 the same shapes run without helpers."""
+    from oracle import c_oracle
+    from tf_seq2seq_losses_b200 import _lib
+    lib = _lib.load()
+    lib.ctcb200_debug_fused_plan(*cfg)
+    old = _lib.DEFAULT_FLAGS
+    _lib.DEFAULT_FLAGS = _lib.FORCE_FUSED
+    fn = _pkg().simple_ctc_loss if variant == SIMPLIFIED else _pkg().classic_ctc_loss
+    try:
+        for (B, T, L, seed) in [(3, 41, 12, 5), (2, 9, 40, 6), (150, 6, 3, 7)]:
+            logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed + V)
+            if L == 40:
+                ll[:] = [4, 40]           # 40 labels over at most 9 frames: infeasible
+            labels[0, 1] = labels[0, 0]   # a repeated token
+            want_loss, want_grad = c_oracle.loss_grad(labels, logits, ll, tl, 0, variant)
+            want_grad[np.isinf(want_loss)] = 0.0
+            weights = np.linspace(0.5, 2.0, B).astype(np.float32)
+            for w in (None, weights):
+                x = _cuda(logits).requires_grad_(True)
+                loss = fn(_cuda(labels), x, _cuda(ll), _cuda(tl), 0)
+                fin = torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss))
+                (fin.sum() if w is None else (fin * _cuda(w)).sum()).backward()
+                _loss_close(loss.detach().cpu().numpy(), want_loss)
+                want = want_grad if w is None else want_grad * w[:, None, None]
+                got = x.grad.cpu().numpy()
+                assert not np.isnan(got).any()
+                assert np.max(np.abs(got - want)) <= GRAD_ATOL_SHORT * (1.0 if w is None else 2.0)
+            # the loss-only call stops at the middle: helpers take part in phase A alone
+            only = fn(_cuda(labels), _cuda(logits), _cuda(ll), _cuda(tl), 0)
+            _loss_close(only.cpu().numpy(), want_loss)
+    finally:
+        _lib.DEFAULT_FLAGS = old
+        lib.ctcb200_debug_fused_plan(0, 0, 0, 0, 0)
+
+
 def test_size_limits_both_paths():
     """The largest label-state count the fused kernel carries (U = 512 -> 16 states per lane) on both device paths, the
     staged kernels beyond it (U = 640 -> 20 per lane, U = 1024 -> 32 per lane, both variants), and a vocabulary whose

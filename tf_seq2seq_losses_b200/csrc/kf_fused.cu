@@ -5,7 +5,7 @@ namespace ctcb200 {
 
 // Developer / test hook (ctcb200_debug_fused_plan in ctc_b200.h): a process-wide override of the plan below.
 static int g_plan_override[5] = {0, 0, 0, 0, 0};     // W, SL, XA, R, mode; W == 0: no override
-void fused_set_plan_override(int W, int SL, int XA, int R, int mode) {     // mode: bit 0 split, 1 no HALF scratch, 2 no idle warps
+void fused_set_plan_override(int W, int SL, int XA, int R, int mode) {     // mode: bit 0 split, 1 no HALF scratch, 2 no idle warps, 3 no row helpers
   const int v[5] = {W, SL, XA, R, mode};
   for (int i = 4; i >= 0; --i) __atomic_store_n(&g_plan_override[i], v[i], __ATOMIC_RELEASE);   // W last
 }
@@ -107,6 +107,16 @@ cudaError_t launch_fused(const Problem& p, const Scratch& s, const float* d_loss
   a.tma = ((p.V & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0) ? 1 : 0;
   if (p.logits_bf16 && (!a.tma || (p.V & 7) != 0)) return cudaErrorInvalidValue;    // checked by the caller (api.cu)
   fused_pick(p, &a.W, &a.SL, &a.XA, &a.R, &a.split, &a.half);
+  // Row helpers: one-CTA plans of wide fp32 rows with at most two workers per side (see fused_layout); the extra barriers
+  // must still fit next to the plan's shared memory.  Debug mode bit 3 switches them off.
+  a.helpers = 0;
+  if (a.W > 0 && !a.split && a.tma && !p.logits_bf16 && fused_helpers_ok(p.V, a.W, a.R, 2) &&
+      !(g_plan_override[4] & 8)) {
+    const int with = fused_layout(p.V, p.Upad, p.S, a.W, a.SL, a.XA, a.R, 2, a.half, 1).total;
+    const int without = fused_layout(p.V, p.Upad, p.S, a.W, a.SL, a.XA, a.R, 2, a.half, 0).total;
+    // the same residency as the plan without them: two CTAs per SM stay two CTAs per SM
+    if (with <= kSmemPerSm && (without > kSmemHalfSm || with <= kSmemHalfSm)) a.helpers = 1;
+  }
   a.rec_alone = (a.split && !(g_plan_override[0] > 0 && (g_plan_override[4] & 4))) ? 1 : 0;     // mode bit 2: off
   (void)W;
   const bool classic = p.variant == CTCB200_CLASSIC;

@@ -286,7 +286,8 @@ __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {      // ro
 struct FusedLayout {
   int W, R, SL, XA;         // workers per side, ring depth (W..2W), row buffers per worker, extra phase-A row buffers (0/1)
   int half;                 // 1: phase A stores every second state row only, phase B derives the others (see HALF below)
-  int off_xch, off_xoff, off_flag, off_side0, total, xch_aliased;
+  int helpers;              // 1: every row worker has a helper warp that takes the upper part of its rows (see helper_phase)
+  int off_xch, off_xoff, off_flag, off_side0, off_hbar, hbar_side_bytes, total, xch_aliased;
   // offsets inside a side block
   int s_ctl, s_bar, s_row, s_aux, s_ringd, s_ringh, side_bytes;
   // offsets inside the aux block (phase B view)
@@ -315,10 +316,22 @@ __host__ __device__ inline int fl_align(int x, int a) { return (x + a - 1) / a *
 __host__ __device__ inline bool fused_half_ok(int S, int W, int R) {
   return CTCB200_HALF_SCRATCH && S == 1 && (W & 1) == 0 && (R & 1) == 0;
 }
+// Row helpers (wide rows, at most two workers per side -- shared memory holds no more at 20 KB a row): a row pass of a
+// single warp is ~3 us at V = 5000 and sets the pace of the whole kernel, so every worker gets a second warp that reduces
+// (phase A) and exponentiates (phase B) the part of the row from float4 `fused_helper_split(n4)` on.  The pair shares the
+// row's TMA barrier; the helper answers through `hdone` (one mbarrier per row buffer and phase) and, in phase A, two
+// floats (`hres`: its maximum and its sum of exponentials).
+__host__ __device__ inline int fused_helper_split(int n4) { return ((n4 >> 1) / (8 * kWarp)) * (8 * kWarp); }
+// (R % W == 0: the frames that share a ring slot belong to one worker, which is what lets the helper wait on the slot's
+// full_d barrier in phase B without ever meeting a later use of it.)
+__host__ __device__ inline bool fused_helpers_ok(int V, int W, int R, int sides) {
+  return sides == 2 && W <= 2 && R % W == 0 && (V & 3) == 0 && fused_helper_split(V >> 2) >= 8 * kWarp;
+}
 __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int W, int SL, int XA, int R, int sides = 2,
-                                                    int half = 0) {
+                                                    int half = 0, int helpers = 0) {
   FusedLayout f;
   f.half = (half && fused_half_ok(S, W, R)) ? 1 : 0;
+  f.helpers = (helpers && fused_helpers_ok(V, W, R, sides)) ? 1 : 0;
   f.W = W;
   f.R = R;
   f.SL = SL;
@@ -350,6 +363,9 @@ __host__ __device__ inline FusedLayout fused_layout(int V, int Upad, int S, int 
   f.side_bytes = fl_align(s, 128);
   f.off_side0 = o;
   f.total = o + sides * f.side_bytes;
+  f.off_hbar = f.total;                                       // per side: hdone[2 phases][W][kMaxRowSlots], hres[W][kMaxRowSlots][2]
+  f.hbar_side_bytes = f.helpers ? 3 * W * kMaxRowSlots * 8 : 0;
+  f.total += sides * f.hbar_side_bytes;
   return f;
 }
 
@@ -363,6 +379,7 @@ struct FusedArgs {
   float* grad;          // [B,T,V]
   int W, SL, XA, R;
   int half;             // 1: HALF state scratch (see fused_layout)
+  int helpers;          // 1: one helper warp per row worker (wide rows, see fused_layout)
   int rec_alone;        // split mode: leave the warps that share the recursion warp's scheduler idle
   int split;            // 1: a cluster of two CTAs per utterance, one per side (small batches); 0: one CTA per utterance
   int tma;              // 1: rows move by 1-D TMA (V % 4 == 0, 16-byte aligned bases); 0: by 4-byte cp.async / plain stores
@@ -387,6 +404,8 @@ struct SideView {
   double* ringc;      // [R]
   float* stbuf;       // [W][S*Upad]
   float* fwd;         // [R/2][Upad]  HALF only
+  unsigned long long* hdone;   // [W][kMaxRowSlots]  helpers only: the helper is through with the row in this buffer
+  float* hres;                 // [W][kMaxRowSlots][2]  helpers only, phase A: the helper's row maximum and sum of exponentials
 };
 
 __device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLayout& f, int side, int phase) {
@@ -406,6 +425,9 @@ __device__ __forceinline__ SideView side_view(unsigned char* smem, const FusedLa
   v.ringc = reinterpret_cast<double*>(base + f.s_aux + f.x_ringc);
   v.stbuf = reinterpret_cast<float*>(base + f.s_aux + f.x_stbuf);
   v.fwd = reinterpret_cast<float*>(base + f.s_aux + f.x_fwd);
+  unsigned char* hb = smem + f.off_hbar + side * f.hbar_side_bytes;
+  v.hdone = reinterpret_cast<unsigned long long*>(hb) + phase * (f.W * kMaxRowSlots);
+  v.hres = reinterpret_cast<float*>(hb + 2 * f.W * kMaxRowSlots * 8);
   return v;
 }
 
@@ -535,6 +557,9 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   constexpr float kLog2e = 1.4426950408889634f;
   const Problem& p = a.p;
   const int W = f.W, R = f.R, V = p.V, Vp = (V + 3) & ~3, n4 = Vp >> 2;
+  // with a helper warp (fused_layout) this warp streams float4 [0, n4m) of its rows and the helper the rest
+  const bool helped = !BF16 && f.helpers;
+  const int n4m = helped ? fused_helper_split(n4) : n4;
   const int SL = PHASE_B ? f.SL : f.SL + f.XA;      // phase A may own one more row buffer (see fused_layout)
   const int n_my = (count > w) ? (count - w + W - 1) / W : 0;
   static_assert(!BF16 || TMA, "bf16 rows move by TMA only");
@@ -622,7 +647,8 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     CTCB200_TRACE("worker %d phase %d frame %d of %d: start (slot %d par %u)", w, (int)PHASE_B, i, count, slot, use_par);
     // ---- prefetch (phase A): the buffer row n-1 used is free as soon as this iteration starts ----
     if (!PHASE_B && n + SL - 1 < n_my) load_row((rs == 0) ? SL - 1 : rs - 1, t + (SL - 1) * W * t_step);
-    TIMED(2, mbar_wait(bars + rs, (par >> rs) & 1u, 3));          // the row has landed
+    const unsigned rowpar = (par >> rs) & 1u;
+    TIMED(2, mbar_wait(bars + rs, rowpar, 3));          // the row has landed
     par ^= 1u << rs;
     float* row = slot_ptr(rs);
     float4* row4 = reinterpret_cast<float4*>(row);
@@ -663,7 +689,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int c4 = base + u * kWarp + lane;
-              v[u] = (!kChecked || c4 < n4) ? row4[c4] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+              v[u] = (!kChecked || c4 < n4m) ? row4[c4] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
             }
           }
           float pm[8];
@@ -681,13 +707,23 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           m_run = mn;
         };
         int base = 0;
-        for (; base + 8 * kWarp <= n4; base += 8 * kWarp) chunk(std::false_type{}, base);
-        if (base < n4) chunk(std::true_type{}, base);
+        for (; base + 8 * kWarp <= n4m; base += 8 * kWarp) chunk(std::false_type{}, base);
+        if (base < n4m) chunk(std::true_type{}, base);
       }
-      const float M = warp_max(m_run);
+      float M = warp_max(m_run), h_max = kNegInf, h_sum = 0.0f;
+      if (helped) {      // the helper's part of the row: its maximum and its sum of exponentials relative to that
+        TIMED(2, mbar_wait(sv.hdone + w * kMaxRowSlots + rs, rowpar, 9));
+        h_max = sv.hres[(w * kMaxRowSlots + rs) * 2];
+        h_sum = sv.hres[(w * kMaxRowSlots + rs) * 2 + 1];
+        M = fmaxf(M, h_max);
+      }
       const float M0 = (M == kNegInf || M == INFINITY) ? 0.0f : M;
       const float mr0 = (m_run == kNegInf || m_run == INFINITY) ? 0.0f : m_run;
-      const float sum = warp_sum(s_run * ex2_approx((mr0 - M0) * kLog2e));
+      float sum = warp_sum(s_run * ex2_approx((mr0 - M0) * kLog2e));
+      if (helped && h_sum > 0.0f) {
+        const float hm0 = (h_max == kNegInf || h_max == INFINITY) ? 0.0f : h_max;
+        sum += h_sum * ex2_approx((hm0 - M0) * kLog2e);
+      }
       lse = fmaf(lg2_approx(sum), 0.6931471805599453f, M0);    // sum is in [1, V]: no denormal / range handling needed
       if (lane == 0 && a.grad != nullptr) a.rowlse[(size_t)b * p.T + t] = lse;
     }
@@ -785,7 +821,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
           __syncwarp();
         } else {
           int c4 = lane;
-          for (; c4 + 3 * kWarp < n4; c4 += 4 * kWarp) {
+          for (; c4 + 3 * kWarp < n4m; c4 += 4 * kWarp) {
             float4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = row4[c4 + u * kWarp];
@@ -794,7 +830,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
 #pragma unroll
             for (int u = 0; u < 4; ++u) row4[c4 + u * kWarp] = v[u];
           }
-          for (; c4 < n4; c4 += kWarp) row4[c4] = fin(row4[c4]);
+          for (; c4 < n4m; c4 += kWarp) row4[c4] = fin(row4[c4]);
         }
       };
       if (dl == 1.0f) softmax_in_place(std::false_type{});     // no upstream gradient (or ones): skip the scaling
@@ -815,6 +851,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
     if (PHASE_B) {
       CTCB200_TRACE("worker %d frame %d: softmax + prefetch done, waiting for the state", w, i);
       TIMED(5, mbar_wait(sv.full_s + slot, use_par, 5));          // the running side's state for this frame is published
+      if (helped) TIMED(5, mbar_wait(sv.hdone + w * kMaxRowSlots + rs, rowpar, 10));   // ... and the helper's part of the row is softmax
       CTCB200_TRACE("worker %d frame %d: state there", w, i);
       const float* other = stb;                                  // the other side's state for this frame
       if (!even_w) {
@@ -996,6 +1033,108 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   if (PHASE_B && tma && lane == 0) bulk_store_wait_read();      // shared memory must outlive the stores reading it
 }
 
+// ---- row helper, one phase (see fused_layout) ---------------------------------------------------------------------------
+// The helper of worker w walks the same rows through the same row buffers, waits on the same landing barrier and handles
+// float4 [fused_helper_split(n4), n4) of every row: their maximum and sum of exponentials in phase A (answered through
+// `hres`), their softmax in place in phase B -- but only once the worker has gathered the frame's label columns from the raw
+// row (it says so on the ring slot's full_d barrier, the one the recursion warp waits on).  `hdone[buffer]` tells the
+// worker the helper is through; the buffer is not reloaded before the worker has seen that, so the helper can never meet
+// a later phase of the landing barrier.  fp32 rows moved by TMA only (no pad lanes, no in-place widening).
+template <bool PHASE_B>
+__device__ __forceinline__ void helper_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int b, int w,
+                                             int count, int t_first, int t_step, float dl, int lane) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  const Problem& p = a.p;
+  const int W = f.W, Vp = (p.V + 3) & ~3, n4 = Vp >> 2, n4m = fused_helper_split(n4);
+  const int SL = PHASE_B ? f.SL : f.SL + f.XA;
+  const int n_my = (count > w) ? (count - w + W - 1) / W : 0;
+  if (!PHASE_B && p.input_logprobas) return;        // no row statistics are taken: the worker does not wait either
+  float* rowbuf = sv.row + (size_t)w * f.SL * Vp;
+  float* rowx = sv.aux_rows + (size_t)w * Vp;
+  unsigned long long* bars = bars_of(sv, w);
+  unsigned long long* hdone = sv.hdone + w * kMaxRowSlots;
+  float* hres = sv.hres + w * kMaxRowSlots * 2;
+  const float* rowlse_b = a.rowlse + (size_t)b * p.T;
+  const bool need_lse = PHASE_B && !p.input_logprobas;
+  float lse_next = (need_lse && n_my > 0) ? rowlse_b[t_first + w * t_step] : 0.0f;
+  int rs = 0;
+  unsigned par = 0;
+  int slot = w % f.R;       // ring slot and use parity of frame i = w + n*W, as in worker_phase
+  unsigned use_par = 0;
+  for (int n = 0; n < n_my; ++n) {
+    const int t = t_first + (w + n * W) * t_step;
+    const float lse = lse_next;
+    if (need_lse && n + 1 < n_my) lse_next = rowlse_b[t + W * t_step];
+    mbar_wait(bars + rs, (par >> rs) & 1u, 11);       // the row has landed
+    par ^= 1u << rs;
+    if (PHASE_B) mbar_wait(sv.full_d + slot, use_par, 12);     // ... and the worker has taken the raw label columns from it
+    float4* row4 = reinterpret_cast<float4*>((rs < f.SL) ? rowbuf + (size_t)rs * Vp : rowx);
+    if (!PHASE_B) {
+      float m_run = kNegInf, s_run = 0.0f;
+      auto chunk = [&](auto checked, int base) {       // the worker's chunk (worker_phase), on the helper's part of the row
+        constexpr bool kChecked = decltype(checked)::value;
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c4 = base + u * kWarp + lane;
+          v[u] = (!kChecked || c4 < n4) ? row4[c4] : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+        }
+        float pm[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) pm[u] = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+        const float cm = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
+        const float mn = fmaxf(m_run, cm);
+        const float mn0 = (mn == kNegInf || mn == INFINITY) ? 0.0f : mn;
+        s_run *= ex2_approx((m_run - mn0) * kLog2e);
+        float ps[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ps[u] = hsum4(exp4_shifted(v[u], mn0));
+        s_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
+        m_run = mn;
+      };
+      int base = n4m;
+      for (; base + 8 * kWarp <= n4; base += 8 * kWarp) chunk(std::false_type{}, base);
+      if (base < n4) chunk(std::true_type{}, base);
+      const float M = warp_max(m_run);
+      const float M0 = (M == kNegInf || M == INFINITY) ? 0.0f : M;
+      const float mr0 = (m_run == kNegInf || m_run == INFINITY) ? 0.0f : m_run;
+      const float sum = warp_sum(s_run * ex2_approx((mr0 - M0) * kLog2e));
+      if (lane == 0) {
+        hres[2 * rs] = M;
+        hres[2 * rs + 1] = sum;
+      }
+    } else {
+      const float2 dl2 = make_float2(dl, dl);
+      const bool scaled = dl != 1.0f;
+      auto fin = [&](float4 v) {
+        float4 e = exp4_shifted(v, lse);
+        if (scaled) {
+          const float2 lo = __fmul2_rn(make_float2(e.x, e.y), dl2), hi = __fmul2_rn(make_float2(e.z, e.w), dl2);
+          e = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+        return e;
+      };
+      int c4 = n4m + lane;
+      for (; c4 + 3 * kWarp < n4; c4 += 4 * kWarp) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = row4[c4 + u * kWarp];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = fin(v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) row4[c4 + u * kWarp] = v[u];
+      }
+      for (; c4 < n4; c4 += kWarp) row4[c4] = fin(row4[c4]);
+      fence_proxy_async();          // this warp's part of the row leaves by the worker's TMA store
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(hdone + rs);
+    slot += W;
+    if (slot >= f.R) { slot -= f.R; use_par ^= 1u; }
+    if (++rs == SL) rs = 0;
+  }
+}
+
 // ---- the kernel body ----------------------------------------------------------------------------------------------------
 // SPLIT = false: one CTA per utterance holds both sides (2 x (1 recursion warp + W workers), W <= 4, two CTAs per SM): the
 //                plan for full batches, where the SMs are shared by two utterances and HBM bandwidth is the limit.
@@ -1009,7 +1148,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const Problem& p = a.p;
-  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA, a.R, SPLIT ? 1 : 2, a.half);
+  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA, a.R, SPLIT ? 1 : 2, a.half, (SPLIT || BF16 || !TMA) ? 0 : a.helpers);
   const int b = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = f.W;
   // Warp -> (side, role); role 0 = recursion warp, 1..W = row workers.  Other placements were measured on B200 (the two
@@ -1021,8 +1160,10 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
   // (For the small one-CTA plans of wide rows -- W = 1 or 2, two CTAs per SM -- shifting the roles of second-wave CTAs by
   // one warp, so that recursion warps and workers of co-resident CTAs do not meet on the same scheduler, was measured at
   // V = 5000: 5.41 ms against 5.06 ms without.  Not done.)
-  const int side = SPLIT ? (int)(blockIdx.x & 1u) : warp / (W + 1);
-  const int role = !SPLIT ? warp % (W + 1) : !a.rec_alone ? warp : (warp == 0) ? 0 : ((warp & 3) == 0) ? -1 : warp - (warp >> 2);
+  // With row helpers a side is 1 + 2W warps: roles W+1 .. 2W are the helpers of workers 1 .. W.
+  const int wps = f.helpers ? 2 * W + 1 : W + 1;      // warps per side (one-CTA plans)
+  const int side = SPLIT ? (int)(blockIdx.x & 1u) : warp / wps;
+  const int role = !SPLIT ? warp % wps : !a.rec_alone ? warp : (warp == 0) ? 0 : ((warp & 3) == 0) ? -1 : warp - (warp >> 2);
   const int my = SPLIT ? 0 : side;        // index of this side's block in THIS CTA's shared memory
   const int L = utt_label_len(p, b), n_t = utt_frames(p, b), M = n_t >> 1;
   const float dl = a.d_loss ? a.d_loss[b] : 1.0f;
@@ -1043,6 +1184,8 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
       const SideView v = side_view(smem, f, s2, 0);      // the two sets are contiguous
       for (int k = 0; k < 2 * 4 * f.R; ++k) mbar_init(v.full_d + k, 1u);
       for (int k = 0; k < 2 * W * kMaxRowSlots; ++k) mbar_init(v.bar + k, TMA ? 1u : (unsigned)kWarp);
+      if (f.helpers)
+        for (int k = 0; k < 2 * W * kMaxRowSlots; ++k) mbar_init(v.hdone + k, 1u);
     }
     fence_mbar_init();
   }
@@ -1205,6 +1348,15 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
     }
   } else if (role < 0) {
     (void)middle();      // an idle warp: the CTA-wide barriers of the middle, nothing else
+  } else if (role > W) {
+    // ---- a row helper (only when f.helpers) ----
+    int cnt, tf;
+    phase_frames(0, cnt, tf);
+    helper_phase<false>(a, f, side_view(smem, f, my, 0), b, role - 1 - W, cnt, tf, ts, dl, lane);
+    if (middle()) {
+      phase_frames(1, cnt, tf);
+      helper_phase<true>(a, f, side_view(smem, f, my, 1), b, role - 1 - W, cnt, tf, ts, dl, lane);
+    }
   } else {
     // ---- a row worker ----
 #pragma unroll 1
@@ -1274,7 +1426,7 @@ static cudaError_t ensure_smem(Kernel kernel, int* cache, int bytes) {
 
 template <int NS, bool CLASSIC, bool TMA, bool BF16>
 static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
-  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA, a.R, a.split ? 1 : 2, a.half);
+  const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA, a.R, a.split ? 1 : 2, a.half, (a.split || BF16 || !TMA) ? 0 : a.helpers);
   // NOTE: a concurrent caller on the same device may raise the attribute between this check and the launch; it is
   // never lowered, so the launch below always finds at least f.total bytes allowed.
   static int cache[2][kMaxDevices];
@@ -1288,7 +1440,7 @@ static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
   } else {
     cudaError_t e = ensure_smem(kf_fused<NS, CLASSIC, TMA, BF16>, cache[0], f.total);
     if (e != cudaSuccess) return e;
-    kf_fused<NS, CLASSIC, TMA, BF16><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
+    kf_fused<NS, CLASSIC, TMA, BF16><<<a.p.B, 2 * (f.helpers ? 2 * a.W + 1 : a.W + 1) * kWarp, f.total, st>>>(a);
   }
   const cudaError_t err = cudaGetLastError();
   if (err == cudaErrorLaunchOutOfResources) {      // say which resource: the plan and the compiled kernel disagree
