@@ -325,8 +325,12 @@ __device__ __forceinline__ void load_state(const float* src, int planes, int lan
   }
 }
 
+// resident CTAs per SM the register-resident form is compiled for (A/B switch, tools/build_variant.sh)
+#ifndef CTCB200_K4_MIN_BLOCKS
+#define CTCB200_K4_MIN_BLOCKS 1
+#endif
 template <int NS, bool CLASSIC, bool HVP>
-__global__ void __launch_bounds__(kK4Warps * kWarp)
+__global__ void __launch_bounds__(kK4Warps * kWarp, CTCB200_K4_MIN_BLOCKS)
     k4_hessian_regs(Problem p, Scratch s, const float* __restrict__ g, float* __restrict__ hessian,
                     const float* __restrict__ d_gradient, float* __restrict__ hvp_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
