@@ -501,7 +501,10 @@ def test_hessian_matches_oracle(variant, k4, monkeypatch):
     The Hessian kernel has a register-resident form (U <= 128) and a generic shared-memory form; both are checked."""
     if k4 == "generic":
         monkeypatch.setenv("CTCB200_K4_GENERIC", "1")
-    for (B, T, V, L, seed) in [(2, 4, 3, 2, 0), (2, 6, 5, 3, 1), (3, 50, 32, 15, 2)]:
+    shapes = [(2, 4, 3, 2, 0), (2, 6, 5, 3, 1), (3, 50, 32, 15, 2)]
+    if k4 == "registers":
+        shapes.append((2, 34, 12, 33, 3))    # two states per lane, every token of the vocabulary several times in the label
+    for (B, T, V, L, seed) in shapes:
         logits, labels, ll, tl = random_inputs(B, T, V, L, seed=seed)
         if T == 6:
             labels[0, :2] = 2           # repeated token
