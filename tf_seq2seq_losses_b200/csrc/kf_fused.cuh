@@ -549,7 +549,7 @@ struct LaneLabels {
 // tok[j] = cleaned label (base_loss.py:395-418) of this lane's states l = lane*NS + j (always a safe column index);
 // `ll` holds their static facts (LaneLabels).  `side` is a runtime argument (one code body for both sides keeps the
 // instruction footprint inside the instruction cache).
-template <int NS, bool CLASSIC, bool PHASE_B, bool TMA, bool BF16>
+template <int NS, bool CLASSIC, bool PHASE_B, bool TMA, bool BF16, bool HELPERS>
 __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayout& f, const SideView& sv, int side, int b,
                                           int w, int count, int t_first, int t_step, int L, double lossd_mid, float dl,
                                           const int (&tok)[NS], const LaneLabels ll, int lane, long long* tm) {
@@ -558,7 +558,7 @@ __device__ __forceinline__ void worker_phase(const FusedArgs& a, const FusedLayo
   const Problem& p = a.p;
   const int W = f.W, R = f.R, V = p.V, Vp = (V + 3) & ~3, n4 = Vp >> 2;
   // with a helper warp (fused_layout) this warp streams float4 [0, n4m) of its rows and the helper the rest
-  const bool helped = !BF16 && f.helpers;
+  const bool helped = HELPERS && f.helpers;
   const int n4m = helped ? fused_helper_split(n4) : n4;
   const int SL = PHASE_B ? f.SL : f.SL + f.XA;      // phase A may own one more row buffer (see fused_layout)
   const int n_my = (count > w) ? (count - w + W - 1) / W : 0;
@@ -1143,12 +1143,15 @@ __device__ __forceinline__ void helper_phase(const FusedArgs& a, const FusedLayo
 //                is the runtime.  Every side gets twice the row workers, its own shared memory and a less crowded
 //                scheduler; the sides only talk at the middle (state vectors through distributed shared memory, two cluster
 //                barriers) and through the global scratch the other side reads back in phase B.
-template <int NS, bool CLASSIC, bool TMA, bool SPLIT, bool BF16>
+// HELPERS: the kernel carries the row helpers' code (a compile-time switch: the extra code cost the narrow-row kernels 1 % at
+// B = 256 and 3 % in the split plan of the classic variant when it was merely branched around -- gpurun_out/p46.txt).
+template <int NS, bool CLASSIC, bool TMA, bool SPLIT, bool BF16, bool HELPERS>
 __device__ __forceinline__ void fused_body(const FusedArgs& a) {
+  static_assert(!HELPERS || (TMA && !SPLIT && !BF16), "row helpers: one-CTA plans of fp32 rows moved by TMA");
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int S = CLASSIC ? 2 : 1, kUpad = NS * kWarp;
   const Problem& p = a.p;
-  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA, a.R, SPLIT ? 1 : 2, a.half, (SPLIT || BF16 || !TMA) ? 0 : a.helpers);
+  const FusedLayout f = fused_layout(p.V, kUpad, S, a.W, a.SL, a.XA, a.R, SPLIT ? 1 : 2, a.half, HELPERS ? a.helpers : 0);
   const int b = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = f.W;
   // Warp -> (side, role); role 0 = recursion warp, 1..W = row workers.  Other placements were measured on B200 (the two
@@ -1184,7 +1187,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
       const SideView v = side_view(smem, f, s2, 0);      // the two sets are contiguous
       for (int k = 0; k < 2 * 4 * f.R; ++k) mbar_init(v.full_d + k, 1u);
       for (int k = 0; k < 2 * W * kMaxRowSlots; ++k) mbar_init(v.bar + k, TMA ? 1u : (unsigned)kWarp);
-      if (f.helpers)
+      if (HELPERS && f.helpers)
         for (int k = 0; k < 2 * W * kMaxRowSlots; ++k) mbar_init(v.hdone + k, 1u);
     }
     fence_mbar_init();
@@ -1348,7 +1351,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
     }
   } else if (role < 0) {
     (void)middle();      // an idle warp: the CTA-wide barriers of the middle, nothing else
-  } else if (role > W) {
+  } else if (HELPERS && role > W) {
     // ---- a row helper (only when f.helpers) ----
     int cnt, tf;
     phase_frames(0, cnt, tf);
@@ -1365,9 +1368,9 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
       phase_frames(ph, cnt, tf);
       const SideView sv = side_view(smem, f, my, ph);
       if (ph == 0) {
-        worker_phase<NS, CLASSIC, false, TMA, BF16>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, ll, lane, tm);
+        worker_phase<NS, CLASSIC, false, TMA, BF16, HELPERS>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, 0.0, dl, tok, ll, lane, tm);
       } else {
-        worker_phase<NS, CLASSIC, true, TMA, BF16>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, ll, lane, tm);
+        worker_phase<NS, CLASSIC, true, TMA, BF16, HELPERS>(a, f, sv, side, b, role - 1, cnt, tf, ts, L, lossd_mid, dl, tok, ll, lane, tm);
         break;
       }
       if (!middle()) {
@@ -1390,14 +1393,14 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a) {
 }
 
 // ---- the two kernels ----------------------------------------------------------------------------------------------------
-template <int NS, bool CLASSIC, bool TMA, bool BF16>
+template <int NS, bool CLASSIC, bool TMA, bool BF16, bool HELPERS>
 __global__ void __launch_bounds__(2 * (kMaxWorkers + 1) * kWarp, (NS <= 8) ? 2 : 1) kf_fused(const __grid_constant__ FusedArgs a) {
-  fused_body<NS, CLASSIC, TMA, false, BF16>(a);
+  fused_body<NS, CLASSIC, TMA, false, BF16, HELPERS>(a);
 }
 template <int NS, bool CLASSIC, bool TMA, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__((NS <= 8) ? 112 : 224)
     kf_fused_split(const __grid_constant__ FusedArgs a) {
-  fused_body<NS, CLASSIC, TMA, true, BF16>(a);
+  fused_body<NS, CLASSIC, TMA, true, BF16, false>(a);
 }
 
 // ---- host side: one launcher per (variant, row-mover) pair, defined in kf_fused_*.cu --------------------------------
@@ -1429,7 +1432,8 @@ static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
   const FusedLayout f = fused_layout(a.p.V, a.p.Upad, a.p.S, a.W, a.SL, a.XA, a.R, a.split ? 1 : 2, a.half, (a.split || BF16 || !TMA) ? 0 : a.helpers);
   // NOTE: a concurrent caller on the same device may raise the attribute between this check and the launch; it is
   // never lowered, so the launch below always finds at least f.total bytes allowed.
-  static int cache[2][kMaxDevices];
+  static int cache[3][kMaxDevices];
+  constexpr bool kCanHelp = TMA && !BF16;      // the only instantiations that carry the row helpers' code
   if (a.split) {
     cudaError_t e = ensure_smem(kf_fused_split<NS, CLASSIC, TMA, BF16>, cache[1], f.total);
     if (e != cudaSuccess) return e;
@@ -1437,16 +1441,21 @@ static cudaError_t launch_fused_ns(const FusedArgs& a, cudaStream_t st) {
     if (a.rec_alone)       // 1 recursion warp + W workers + the idle warps 4, 8, ... in between
       for (warps = 1; warps - 1 - (warps - 1) / 4 < a.W; ++warps) {}
     kf_fused_split<NS, CLASSIC, TMA, BF16><<<2 * a.p.B, warps * kWarp, f.total, st>>>(a);
-  } else {
-    cudaError_t e = ensure_smem(kf_fused<NS, CLASSIC, TMA, BF16>, cache[0], f.total);
+  } else if (kCanHelp && f.helpers) {
+    cudaError_t e = ensure_smem(kf_fused<NS, CLASSIC, TMA, BF16, kCanHelp>, cache[2], f.total);
     if (e != cudaSuccess) return e;
-    kf_fused<NS, CLASSIC, TMA, BF16><<<a.p.B, 2 * (f.helpers ? 2 * a.W + 1 : a.W + 1) * kWarp, f.total, st>>>(a);
+    kf_fused<NS, CLASSIC, TMA, BF16, kCanHelp><<<a.p.B, 2 * (2 * a.W + 1) * kWarp, f.total, st>>>(a);
+  } else {
+    cudaError_t e = ensure_smem(kf_fused<NS, CLASSIC, TMA, BF16, false>, cache[0], f.total);
+    if (e != cudaSuccess) return e;
+    kf_fused<NS, CLASSIC, TMA, BF16, false><<<a.p.B, 2 * (a.W + 1) * kWarp, f.total, st>>>(a);
   }
   const cudaError_t err = cudaGetLastError();
   if (err == cudaErrorLaunchOutOfResources) {      // say which resource: the plan and the compiled kernel disagree
     cudaFuncAttributes fa{};
     if (a.split) (void)cudaFuncGetAttributes(&fa, kf_fused_split<NS, CLASSIC, TMA, BF16>);
-    else (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA, BF16>);
+    else if (kCanHelp && f.helpers) (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA, BF16, kCanHelp>);
+    else (void)cudaFuncGetAttributes(&fa, kf_fused<NS, CLASSIC, TMA, BF16, false>);
     fprintf(stderr, "libctc_b200: kf_fused%s<NS=%d,classic=%d,tma=%d> bf16=%d W=%d SL=%d XA=%d R=%d: %d threads, %d B dynamic smem; kernel: %d regs, "
             "max %d threads/block, %zu B static smem, %d B max dynamic smem, %zu B local\n", a.split ? "_split" : "", NS, (int)CLASSIC,
             (int)TMA, (int)BF16, a.W, a.SL, a.XA, a.R, (a.split ? 1 : 2) * (a.W + 1) * kWarp, f.total, fa.numRegs, fa.maxThreadsPerBlock,
