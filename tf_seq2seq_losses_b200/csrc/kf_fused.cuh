@@ -1144,7 +1144,7 @@ __device__ __forceinline__ void helper_phase(const FusedArgs& a, const FusedLayo
 //                scheduler; the sides only talk at the middle (state vectors through distributed shared memory, two cluster
 //                barriers) and through the global scratch the other side reads back in phase B.
 // HELPERS: the kernel carries the row helpers' code (a compile-time switch: the extra code cost the narrow-row kernels 1 % at
-// B = 256 and 3 % in the split plan of the classic variant when it was merely branched around -- gpurun_out/p46.txt).
+// B = 256 and 3 % in the split plan of the classic variant when it was merely branched around -- profiles/r2_ab_helper_code_cost.txt).
 template <int NS, bool CLASSIC, bool TMA, bool SPLIT, bool BF16, bool HELPERS>
 __device__ __forceinline__ void fused_body(const FusedArgs& a) {
   static_assert(!HELPERS || (TMA && !SPLIT && !BF16), "row helpers: one-CTA plans of fp32 rows moved by TMA");
