@@ -7,7 +7,7 @@ legs of ``bench.py``.
 Parity status: PINNED.  The reference is pure Python over TensorFlow and TensorFlow is not installable in
 this image; its own code is nevertheless executed here with ``tensorflow`` served by a numpy implementation
 of the ops it calls (``tests/golden/tf_numpy_shim.py``), and this restatement reproduces the outputs of that
-run -- loss, gradient, alpha, beta, Hessian, gamma -- bit for bit (``tests/golden/reference_outputs.npz``,
+run -- loss, gradient, alpha, beta, Hessian, gamma -- bit for bit (``tests/golden/reference/reference_outputs.npz``,
 ``tests/test_reference_golden.py``).  It is also pinned against
 every literal known-answer test the reference's own test-suite holds for the path (see
 ``tests/test_oracle_kats.py``; the vectors are re-expressed there with the reference file:line), against

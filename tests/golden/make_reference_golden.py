@@ -1,4 +1,4 @@
-"""Generates tests/golden/reference_outputs.npz by running the REFERENCE'S OWN CODE (/root/reference/tf_seq2seq_losses,
+"""Generates tests/golden/reference/reference_outputs.npz by running the REFERENCE'S OWN CODE (/root/reference/tf_seq2seq_losses,
 imported unmodified) on small seeded inputs.  TensorFlow cannot be installed in this image, so ``tensorflow`` is served
 by tests/golden/tf_numpy_shim.py, a numpy implementation of the TensorFlow ops the reference calls; the reference's
 Python -- the label cleaning, the masks, the tf.while_loop recursions, the transition tables, the token scatter, the
@@ -26,7 +26,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE = "/root/reference"
-OUT = os.path.join(HERE, "reference_outputs.npz")
+OUT = os.path.join(HERE, "reference", "reference_outputs.npz")     # its own directory: tests/test_golden.py globs tests/golden/*.npz
 
 # name: (B, T, V, Lw, blank, seed, with_second_order)
 CASES = {

@@ -1,6 +1,6 @@
 """Parity against outputs of the REFERENCE ITSELF.
 
-tests/golden/reference_outputs.npz holds what /root/reference/tf_seq2seq_losses computes -- its own Python, imported
+tests/golden/reference/reference_outputs.npz holds what /root/reference/tf_seq2seq_losses computes -- its own Python, imported
 unmodified, with TensorFlow served by the numpy shim tests/golden/tf_numpy_shim.py -- for the seeded inputs of
 tests/golden/make_reference_golden.py: the data classes' loss / gradient / logarithmic_logproba_gradient / alpha / beta /
 hessian / gamma (base_loss.py:186-298, classic_ctc_loss.py, simplified_ctc_loss.py) and the loss of the public functions
@@ -21,7 +21,7 @@ import pytest
 from oracle import ctc_oracle as orc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURE = os.path.join(HERE, "golden", "reference_outputs.npz")
+FIXTURE = os.path.join(HERE, "golden", "reference", "reference_outputs.npz")
 CASE_NAMES = ["small_ragged", "repeats", "blank_mid", "blank_last_empty_label", "labels_wider_than_needed", "mid"]
 VARIANTS = [("classic", orc.CLASSIC), ("simplified", orc.SIMPLIFIED)]
 FIRST_ORDER = ["loss", "gradient", "logarithmic_logproba_gradient", "alpha", "beta"]
