@@ -21,7 +21,22 @@ import types
 
 import numpy as np
 
-Tensor = np.ndarray
+class Tensor(np.ndarray):
+    """A numpy array that also answers ``.numpy()`` (the reference's own tests call it); arithmetic, comparisons and slices
+    of a Tensor stay Tensors, and an element access gives a 0-d Tensor instead of a numpy scalar."""
+
+    def numpy(self):
+        return np.asarray(self)
+
+    def __getitem__(self, key):
+        r = super().__getitem__(key)
+        return r if isinstance(r, np.ndarray) else np.asarray(r).view(Tensor)
+
+
+def _t(x):
+    return np.asarray(x).view(Tensor)
+
+
 int32 = np.dtype(np.int32)
 int64 = np.dtype(np.int64)
 bool = np.dtype(np.bool_)          # noqa: A001  (tf.bool)
@@ -164,13 +179,38 @@ def reduce_sum(input_tensor, axis=None, keepdims=False):
     return np.sum(input_tensor, axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims)
 
 
+def _axis(axis):
+    return tuple(axis) if isinstance(axis, list) else axis
+
+
 def reduce_max(input_tensor, axis=None, keepdims=False):
-    return np.max(input_tensor, axis=axis, keepdims=keepdims)
+    return np.max(input_tensor, axis=_axis(axis), keepdims=keepdims)
+
+
+def reduce_mean(input_tensor, axis=None, keepdims=False):
+    return np.mean(input_tensor, axis=_axis(axis), keepdims=keepdims)
+
+
+def reduce_all(input_tensor, axis=None, keepdims=False):
+    return np.all(input_tensor, axis=_axis(axis), keepdims=keepdims)
+
+
+def abs(x):                        # noqa: A001
+    return np.abs(x)
+
+
+def norm(tensor, ord="euclidean", axis=None):   # noqa: A002
+    x = np.asarray(tensor)
+    if ord == np.inf:
+        return np.max(np.abs(x), axis=_axis(axis))
+    assert ord in ("euclidean", 2)
+    return np.sqrt(np.sum(x * x, axis=_axis(axis)))
 
 
 def reduce_logsumexp(input_tensor, axis=None, keepdims=False):
     """tf.reduce_logsumexp: log(sum(exp(x - m))) + m with m = max where that is finite, else 0."""
     x = np.asarray(input_tensor)
+    axis = _axis(axis)
     with np.errstate(all="ignore"):
         raw = np.max(x, axis=axis, keepdims=True)
         m = np.where(np.isfinite(raw), raw, np.zeros_like(raw))
@@ -232,10 +272,10 @@ class TensorArray:
         return self
 
     def read(self, index):
-        return self._items[_i(index)]
+        return _t(self._items[_i(index)])
 
     def stack(self):
-        return np.stack(self._items, axis=0)
+        return _t(np.stack(self._items, axis=0))
 
 
 def while_loop(cond, body, loop_vars, maximum_iterations=None, swap_memory=False, name=None):   # noqa: A002
@@ -294,9 +334,65 @@ def _set_diag(input, diagonal):    # noqa: A002
     return out
 
 
+# ---- only the reference's own TESTS need what follows (tests/golden/run_reference_tests.py) ----
+_rng = np.random.default_rng(0)
+
+
+def _set_seed(seed):
+    global _rng
+    _rng = np.random.default_rng(seed)
+
+
+def _random_normal(shape, mean=0.0, stddev=1.0, dtype=None):   # noqa: A002
+    return (_rng.standard_normal(_shape(shape)) * stddev + mean).astype(float32 if dtype is None else dtype)
+
+
+def _random_uniform(shape, minval=0, maxval=None, dtype=None):   # noqa: A002
+    dtype = np.dtype(float32 if dtype is None else dtype)
+    if dtype.kind in "iu":
+        return _rng.integers(minval, maxval, size=_shape(shape)).astype(dtype)
+    return (_rng.random(_shape(shape)) * ((1.0 if maxval is None else maxval) - minval) + minval).astype(dtype)
+
+
+def function(func=None, **kwargs):     # tf.function: eager execution is all there is
+    return func if func is not None else (lambda f: f)
+
+
+def TensorSpec(shape=None, dtype=None, name=None):   # noqa: N802, A002
+    return (shape, dtype)
+
+
 math = types.SimpleNamespace(log=_log, softplus=_softplus, expm1=_expm1, exp=exp, unsorted_segment_max=_unsorted_segment_max,
                              unsorted_segment_sum=_unsorted_segment_sum)
 linalg = types.SimpleNamespace(band_part=_band_part, set_diag=_set_diag)
+
+
+random = types.SimpleNamespace(set_seed=_set_seed, normal=_random_normal, uniform=_random_uniform)
+
+
+def _as_tensor_result(f):
+    """Results leave the shim as Tensor views (so that ``.numpy()`` works on them); the values are untouched."""
+    def g(*args, **kwargs):
+        r = f(*args, **kwargs)
+        if isinstance(r, (np.ndarray, np.generic)):
+            return _t(r)
+        if isinstance(r, list):
+            return [_t(v) for v in r]
+        return r
+    g.__name__ = getattr(f, "__name__", "op")
+    g.__doc__ = f.__doc__
+    return g
+
+
+for _name in ("constant", "convert_to_tensor", "cast", "shape", "reshape", "transpose", "expand_dims", "squeeze", "stack",
+              "concat", "tile", "roll", "pad", "zeros", "ones", "zeros_like", "ones_like", "eye", "range", "one_hot",
+              "sequence_mask", "where", "exp", "reduce_sum", "reduce_max", "reduce_mean", "reduce_all", "reduce_logsumexp",
+              "abs", "norm", "cumsum", "meshgrid", "gather", "scatter_nd"):
+    globals()[_name] = _as_tensor_result(globals()[_name])
+for _ns in (math, linalg, random):
+    for _name, _f in list(vars(_ns).items()):
+        if callable(_f) and _name != "set_seed":
+            setattr(_ns, _name, _as_tensor_result(_f))
 
 
 def install(float_dtype=np.float32):

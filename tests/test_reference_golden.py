@@ -88,6 +88,19 @@ def test_fixture_is_what_the_reference_computes_here():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="the reference sources are not on this machine")
+def test_the_shim_passes_the_reference_own_unit_tests():
+    """The reference's own test modules, unmodified, against its own code on the numpy shim: every test that does not need
+    TensorFlow's autodiff / tf.nn.ctc_loss passes -- the literal alpha / beta tables, the exact 0 / 100.0 / 1e10 / +inf
+    losses, the exact gradients, the tools.py examples.  This is what licenses the shim as a stand-in for TensorFlow here."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "run_reference_tests.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    summary = r.stdout.strip().splitlines()[-1]
+    n_pass = int(summary.split(":")[1].split("passed")[0])
+    assert n_pass >= 28 and " 0 failed" in summary, summary
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag,variant", VARIANTS)
 @pytest.mark.parametrize("name", CASE_NAMES)
