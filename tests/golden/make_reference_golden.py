@@ -111,6 +111,40 @@ def build():
     return flat
 
 
+def check_oracle_made_fixtures():
+    """tests/golden/*.npz were written by the oracle (make_golden.py).  Here the reference computes the same quantities for
+    their inputs; returns the list of (file, key, max abs difference) that exceed 1e-12."""
+    import glob
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import tf_numpy_shim
+    tf_numpy_shim.install(np.float64)
+    if REFERENCE not in sys.path:
+        sys.path.append(REFERENCE)
+    from tf_seq2seq_losses.classic_ctc_loss import ClassicCtcLossData
+    from tf_seq2seq_losses.simplified_ctc_loss import SimplifiedCtcLossData
+    from tf_seq2seq_losses.tools import logit_to_logproba
+    bad, n = [], 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for path in sorted(glob.glob(os.path.join(HERE, "*.npz"))):
+            z = np.load(path)
+            logprobas = logit_to_logproba(logit=z["logits"].astype(np.float64), axis=2)
+            for tag, cls in (("classic", ClassicCtcLossData), ("simplified", SimplifiedCtcLossData)):
+                data = cls(labels=z["labels"], logprobas=logprobas, label_length=z["label_length"],
+                           logit_length=z["logit_length"], blank_index=int(z["blank"]))
+                for key in ("loss", "gradient", "alpha", "beta", "hessian"):
+                    if f"{tag}_{key}" not in z.files:
+                        continue
+                    got, want = np.asarray(getattr(data, key)), z[f"{tag}_{key}"]
+                    fin = np.isfinite(want)
+                    diff = float(np.max(np.abs(got[fin] - want[fin]))) if fin.any() else 0.0
+                    n += 1
+                    if got.shape != want.shape or not np.array_equal(got[~fin], want[~fin]) or diff > 1e-12:
+                        bad.append((os.path.basename(path), f"{tag}_{key}", diff))
+    return n, bad
+
+
 def main():
     flat = build()
     if "--check" in sys.argv:       # the committed fixture is what the reference computes here: every array, bit for bit
@@ -118,7 +152,9 @@ def main():
         bad = [k for k in flat if k not in stored.files or not np.array_equal(np.asarray(flat[k]), stored[k], equal_nan=True)]
         bad += [k for k in stored.files if k not in flat]
         print(f"{len(flat)} arrays regenerated from {REFERENCE}; mismatches: {bad}")
-        sys.exit(1 if bad else 0)
+        n, bad2 = check_oracle_made_fixtures()
+        print(f"{n} arrays of the oracle-made fixtures tests/golden/*.npz recomputed by the reference; beyond 1e-12: {bad2}")
+        sys.exit(1 if bad or bad2 else 0)
     np.savez_compressed(OUT, **flat)
     print(f"wrote {OUT}: {len(flat)} arrays, {os.path.getsize(OUT) / 1024:.0f} KB")
 

@@ -1,4 +1,6 @@
-"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the float64 oracle).
+"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the float64 oracle and
+re-computed by the REFERENCE'S OWN CODE -- every loss / gradient / alpha / beta / Hessian array within 1e-12 -- by
+`tests/golden/make_reference_golden.py --check`, which tests/test_reference_golden.py runs wherever /root/reference exists).
 CPU: the oracle and its C port still reproduce them.  GPU: the CUDA path matches them."""
 import glob
 import os
