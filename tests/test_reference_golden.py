@@ -22,7 +22,7 @@ from oracle import ctc_oracle as orc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIXTURE = os.path.join(HERE, "golden", "reference", "reference_outputs.npz")
-CASE_NAMES = ["small_ragged", "repeats", "blank_mid", "blank_last_empty_label", "labels_wider_than_needed", "mid"]
+CASE_NAMES = ["small_ragged", "repeats", "blank_mid", "blank_last_empty_label", "labels_wider_than_needed", "mid", "long"]
 VARIANTS = [("classic", orc.CLASSIC), ("simplified", orc.SIMPLIFIED)]
 FIRST_ORDER = ["loss", "gradient", "logarithmic_logproba_gradient", "alpha", "beta"]
 
@@ -118,8 +118,9 @@ def test_cuda_path_matches_the_reference_outputs(name, tag, variant):
     assert np.array_equal(np.isinf(got_loss), np.isinf(want_loss))
     fin = np.isfinite(want_loss)
     assert np.all(np.abs(got_loss[fin] - want_loss[fin]) <= 1e-5 * np.maximum(1.0, np.abs(want_loss[fin])))
-    # gradient / Hessian w.r.t. log-probabilities: absolute tolerances of tests/test_cuda_parity.py
-    for key, atol in (("gradient", 5e-5), ("hessian", 5e-5)):
+    # gradient / Hessian w.r.t. log-probabilities: absolute tolerances of tests/test_cuda_parity.py (5e-4 beyond 64 frames)
+    grad_atol = 5e-5 if logits.shape[1] <= 64 else 5e-4
+    for key, atol in (("gradient", grad_atol), ("hessian", 5e-5)):
         want = ref(tag, key)
         if want is not None:
             got = getattr(data, key).cpu().numpy().astype(np.float64)
@@ -128,6 +129,8 @@ def test_cuda_path_matches_the_reference_outputs(name, tag, variant):
     # alpha / beta: -inf exactly where the reference has it, finite values to 1e-5 relative
     for key in ("alpha", "beta"):
         want = ref(tag, key)
+        if want is None:
+            continue
         got = getattr(data, key).cpu().numpy().astype(np.float64)
         assert got.shape == want.shape
         assert np.array_equal(np.isinf(got), np.isinf(want)), key
@@ -152,4 +155,4 @@ def test_cuda_path_matches_the_reference_outputs(name, tag, variant):
     assert np.all(np.abs(got_loss[fin] - want_loss[fin]) <= 1e-5 * np.maximum(1.0, np.abs(want_loss[fin])))
     want_grad = _grad_logits_from(ref(tag, "gradient"), logits)
     want_grad[np.isinf(want_loss)] = 0.0
-    assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= 5e-5
+    assert np.max(np.abs(x.grad.cpu().numpy() - want_grad)) <= grad_atol
