@@ -37,6 +37,9 @@ CASES = {
     "labels_wider_than_needed": (2, 10, 6, 6, 0, 13, True),
     "mid": (3, 40, 12, 10, 0, 17, False),
     "long": (2, 300, 40, 60, 0, 19, False),          # first-order outputs only, no state tensors (fixture size)
+    # undefined input with definite arithmetic: a real label EQUAL to the blank (base_loss.py:328-344 gathers its
+    # log-probability like any token's; classic_ctc_loss.py:647-654 overrides the blank column of the gradient)
+    "label_equals_blank": (3, 9, 5, 4, 1, 23, True),
 }
 
 
@@ -60,6 +63,12 @@ def make_inputs(name):
         label_length[0] = 0                                  # empty label: every frame is blank
         logit_length[2] = 0                                  # no frames at all
         label_length[2] = 0
+    if name == "label_equals_blank":
+        labels[0, 1] = blank
+        labels[1, 0] = blank
+        labels[1, 2] = blank
+        label_length[:] = [3, 4, 2]
+        logit_length[:] = [9, 8, 6]
     if name == "long":
         label_length[:] = [60, 41]
         logit_length[:] = [300, 233]
@@ -149,7 +158,51 @@ def check_oracle_made_fixtures():
     return n, bad
 
 
+def fuzz(trials, seed=0):
+    """Random small problems (every blank position, repeated tokens, ragged / infeasible / empty lengths): the oracle against
+    the reference, every data-class output, at 1e-12.  Returns the failures."""
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))       # the repo root, for `oracle`
+    from oracle import ctc_oracle as orc
+    import tf_numpy_shim
+    tf_numpy_shim.install(np.float64)
+    if REFERENCE not in sys.path:
+        sys.path.append(REFERENCE)
+    from tf_seq2seq_losses.classic_ctc_loss import ClassicCtcLossData
+    from tf_seq2seq_losses.simplified_ctc_loss import SimplifiedCtcLossData
+    rng = np.random.default_rng(seed)
+    bad = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for trial in range(trials):
+            B, T, V, Lw = int(rng.integers(1, 4)), int(rng.integers(1, 12)), int(rng.integers(2, 7)), int(rng.integers(1, 6))
+            blank = int(rng.integers(0, V))
+            x = rng.standard_normal((B, T, V)) * rng.choice([0.3, 1.0, 5.0])
+            logprobas = x - np.log(np.sum(np.exp(x), axis=2, keepdims=True))
+            others = [k for k in range(V) if k != blank]
+            labels = rng.choice(others, size=(B, Lw)).astype(np.int32)
+            ll = rng.integers(0, Lw + 1, size=B).astype(np.int32)
+            tl = rng.integers(0, T + 1, size=B).astype(np.int32)
+            for tag, cls, variant in (("classic", ClassicCtcLossData, orc.CLASSIC), ("simplified", SimplifiedCtcLossData, orc.SIMPLIFIED)):
+                ref = cls(labels=labels, logprobas=logprobas, label_length=ll, logit_length=tl, blank_index=blank)
+                mine = orc.CtcLossData(labels, logprobas, ll, tl, blank, variant)
+                for key in ("loss", "gradient", "logarithmic_logproba_gradient", "alpha", "beta", "hessian", "gamma"):
+                    got, want = np.asarray(getattr(mine, key), dtype=np.float64), np.asarray(getattr(ref, key), dtype=np.float64)
+                    fin = np.isfinite(want)
+                    ok = got.shape == want.shape and np.array_equal(got[~fin], want[~fin]) and \
+                        (not fin.any() or float(np.max(np.abs(got[fin] - want[fin]))) <= 1e-12)
+                    if not ok:
+                        bad.append((trial, tag, key, (B, T, V, Lw, blank), ll.tolist(), tl.tolist()))
+    return bad
+
+
 def main():
+    if "--fuzz" in sys.argv:
+        n = int(sys.argv[sys.argv.index("--fuzz") + 1])
+        bad = fuzz(n)
+        print(f"{n} random problems x 2 variants x 7 outputs, oracle against the reference at 1e-12; failures: {bad}")
+        sys.exit(1 if bad else 0)
     flat = build()
     if "--check" in sys.argv:       # the committed fixture is what the reference computes here: every array, bit for bit
         stored = np.load(OUT)

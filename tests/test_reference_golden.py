@@ -23,6 +23,10 @@ from oracle import ctc_oracle as orc
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIXTURE = os.path.join(HERE, "golden", "reference", "reference_outputs.npz")
 CASE_NAMES = ["small_ragged", "repeats", "blank_mid", "blank_last_empty_label", "labels_wider_than_needed", "mid", "long"]
+# a real label equal to the blank -- undefined input whose arithmetic in the reference is nevertheless definite: pinned on the
+# CPU here; the CUDA path's agreement with the oracle on it is tests/test_cuda_parity.py::
+# test_real_label_equal_to_blank_matches_reference_semantics
+CPU_ONLY_CASES = ["label_equals_blank"]
 VARIANTS = [("classic", orc.CLASSIC), ("simplified", orc.SIMPLIFIED)]
 FIRST_ORDER = ["loss", "gradient", "logarithmic_logproba_gradient", "alpha", "beta"]
 
@@ -57,7 +61,7 @@ def _grad_logits_from(gradient_logproba, logits):
 
 
 @pytest.mark.parametrize("tag,variant", VARIANTS)
-@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("name", CASE_NAMES + CPU_ONLY_CASES)
 def test_oracle_reproduces_the_reference_outputs(name, tag, variant):
     (logits, labels, ll, tl, blank), ref = _load(name)
     logprobas = orc.logit_to_logproba(logits.astype(np.float64))
@@ -86,6 +90,15 @@ def test_fixture_is_what_the_reference_computes_here():
     r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), "--check"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tf_seq2seq_losses"), reason="the reference sources are not on this machine")
+def test_oracle_equals_the_reference_on_random_problems():
+    """200 random small problems (every blank position, ragged / infeasible / empty lengths): loss, gradient, logarithmic
+    gradient, alpha, beta, Hessian and gamma of the oracle against the reference's own code, at 1e-12."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), "--fuzz", "200"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="the reference sources are not on this machine")
