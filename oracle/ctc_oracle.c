@@ -3,7 +3,8 @@
  *
  * TEST INFRASTRUCTURE ONLY: used by tests/ as a full-size checker and by bench.py's cpu_baseline / --impl reference
  * legs.  The product (tf_seq2seq_losses_b200/) never links or loads it.  Pinned against the numpy oracle
- * (oracle/ctc_oracle.py, itself pinned against the reference's known-answer tests) in tests/test_oracle_c.py.
+ * (oracle/ctc_oracle.py, itself pinned against the reference's known-answer tests) in tests/test_oracle_c.py, and against
+ * outputs of the reference's own code (tests/golden/reference/reference_outputs.npz) in tests/test_reference_golden.py.
  *
  * Exposes ctc_oracle_loss_grad_f64 (double arithmetic, the checker) and ctc_oracle_loss_grad_f32 (float arithmetic,
  * like the reference, which asserts float32: tf_seq2seq_losses/base_loss.py:131).
